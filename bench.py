@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Headline benchmark: fused kernel-matrix matmat throughput in Gentries/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|c3_laplace|c3_matern52|small] [--no-cpu-baseline]
+
+A *step* is one pass of the hot path ``Y = K(X, X) @ V`` over the whole synthetic
+problem (BASELINE.json configs[1]: RBF, n = m = 1M, d = 128, k = 64, fp32); one
+"entry" is one K_ij evaluated and contracted with the k columns of V.  Under
+``torchrun`` (N > 1) the rows of K are partitioned over the ranks
+(``torch.chunk``), X and V are replicated, and every step ends with the
+all-gather of the row blocks, so ``value`` is whole-job throughput at fixed total
+work (strong scaling).
+
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides,
+max over ranks; inputs (768 MB) exceed L2 so no flush is needed; nvidia-smi clocks
+are sampled during the timed region.
+
+``--impl reference`` times the reference's CPU path for the same metric: the
+reference's kernel arithmetic lives in PyKeOps (not installable here), so the arm
+runs the oracle's dense-torch restatement of the reference formulas on all host
+cores over a bounded row sample (kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kernel, n, d, k)
+    "c2": ("rbf", 1_000_000, 128, 64),
+    "c3_laplace": ("laplace", 4_000_000, 32, 16),
+    "c3_matern52": ("matern52", 4_000_000, 32, 16),
+    "small": ("rbf", 65_536, 128, 64),
+}
+SM_COUNT_B200 = 148
+FP32_LANES_PER_SM = 128
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        p["_source"] = "measured"
+        return p
+    # fallback stated in B200_PROFILING.md
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0,
+            "_source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.rows, self.proc, self.thread = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def make_data(kernel: str, n: int, d: int, k: int):
+    """Synthetic Gaussian data of SURVEY §8d: X = randn(n, d)/sqrt(d), V = randn(n, k), seed 0, made on the CPU."""
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(n, d, generator=g) / d**0.5
+    V = torch.randn(n, k, generator=g)
+    return X, V
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def cpu_baseline(kernel: str, X: torch.Tensor, V: torch.Tensor, budget_s: float = 15.0, max_rows: int = 8192) -> dict:
+    """Oracle ("port" of the reference formulas) on all host cores over a bounded row sample."""
+    from oracle import kernel_oracle as ko
+
+    n = X.shape[0]
+    fn = ko.kernel_matmat if kernel == "laplace" else ko.kernel_matmat_gemm_form
+    probe = 128
+    t0 = time.perf_counter()
+    fn(X[:probe], X, V, kernel, 1.0)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    rows = int(min(max_rows, max(probe, budget_s / dt * probe), n))
+    t0 = time.perf_counter()
+    fn(X[:rows], X, V, kernel, 1.0)
+    dt = time.perf_counter() - t0
+    form = "direct-difference" if kernel == "laplace" else "GEMM-form"
+    return {
+        "value": rows * n / dt / 1e9,
+        "unit": "Gentries/s",
+        "cores": torch.get_num_threads(),
+        "kind": "port",
+        "sample": f"K(X[:{rows}], X) @ V, {form} fp32 torch on CPU, {dt:.1f} s",
+        "seconds": dt,
+    }
+
+
+def run_reference(args) -> int:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    kernel, n, d, k = WORKLOADS[args.workload]
+    X, V = make_data(kernel, n, d, k)
+    vals, base = [], None
+    for i in range(args.warmup + args.steps):
+        base = cpu_baseline(kernel, X, V, budget_s=args.ref_budget_s)
+        if i >= args.warmup:
+            vals.append(base)
+    value = statistics.mean(b["value"] for b in vals)
+    ms = statistics.mean(b["seconds"] for b in vals) * 1e3
+    line = {
+        "impl": "reference",
+        "metric": "kernel_matmat_gentries_per_s",
+        "value": value,
+        "unit": "Gentries/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": _config(args.workload, kernel, n, d, k, args.gpus),
+        "cpu_baseline": {kk: (value if kk == "value" else vv) for kk, vv in base.items() if kk != "seconds"},
+        "e2e": {"value": value, "unit": "Gentries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def _config(workload, kernel, n, d, k, gpus):
+    return {
+        "workload": f"{workload}: {kernel} kernel matmat K(X,X)@V, n=m={n}, d={d}, k={k}, fp32, lengthscale=1.0",
+        "n": n, "m": n, "d": d, "k": k, "kernel": kernel,
+        "parallelism": f"row-partition x{gpus} (A2, V replicated; all-gather of row blocks)" if gpus > 1 else "single GPU",
+        "l2": "inputs (X+V) exceed the 126 MB L2; no flush between iterations",
+    }
+
+
+# ----------------------------------------------------------------------------- ours
+def run_ours(args) -> int:
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the kernel-matmat path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import rlaopt_b200  # noqa: F401  loads the C-ABI extension
+    from rlaopt_b200 import _lib, ops
+    from rlaopt_b200.kernels import KernelConfig
+    from rlaopt_b200.kernels.base import _KernelLinOp
+    from rlaopt_b200.kernels.sharded import sharded_kernel_linop
+
+    _lib.load()
+    kernel, n, d, k = WORKLOADS[args.workload]
+    X, V = make_data(kernel, n, d, k)
+    Xp, Vp = X.pin_memory(), V.pin_memory()
+    cfg = KernelConfig(lengthscale=1.0)
+
+    def build(Xh):
+        Xg = Xh.to(dev, non_blocking=True)
+        if world > 1:
+            return sharded_kernel_linop(Xg, Xg, cfg, kernel, dev)
+        return _KernelLinOp(Xg, Xg, cfg, _kernel_key=kernel)
+
+    op = build(Xp)
+    Vg = Vp.to(dev)
+    layout = ops.choose_layout(ops.kernel_id(kernel), torch.float32, d, k)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for _ in range(args.warmup):
+        Y = op @ Vg
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.LAUNCH_COUNT
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for a, b in evs:
+        a.record()
+        Y = op @ Vg
+        b.record()
+    stop.record()
+    sync_all()
+    launches = ops.LAUNCH_COUNT - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = start.elapsed_time(stop)
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    t = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = t.item()
+    ms_per_step = total_ms / args.steps
+    value = n * n / (ms_per_step * 1e-3) / 1e9
+    checksum = float(Y.double().abs().sum().item())
+
+    # ---- end to end through the public API with host buffers ----------------------------------
+    Yh = torch.empty((n, k), dtype=torch.float32).pin_memory()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def e2e_step():
+        op_e = build(Xp)  # H2D of X, operator construction (packing happens on first product)
+        Yd = op_e @ Vp.to(dev, non_blocking=True)  # H2D of V, fused matmat (+ all-gather)
+        Yh.copy_(Yd, non_blocking=True)  # D2H of the result
+        torch.cuda.synchronize(dev)
+
+    e2e_step()  # warm
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    sync_all()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = n * n / e2e_s.item() / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peaks = _peaks()
+    rows_per_rank = -(-n // world)
+    flops_per_launch = rows_per_rank * n * (2 * d + 2 * k)  # algorithmic: 2d + 2k flop per entry
+    kernel_ms = statistics.mean(step_ms)  # the fused kernel is the step (pack is cached, gather is <1%)
+    achieved = flops_per_launch / (kernel_ms * 1e-3) / 1e12
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    ffma_peak = SM_COUNT_B200 * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12
+    if layout == _lib.LAYOUT_TC:
+        # fp16 hi/lo split for X.X^T (3 MMAs at the bf16 rate) + TF32 hi/lo split for P.V (3 MMAs at half rate):
+        # tensor work = 6d + 12k bf16-equivalent flop per entry for 2d + 2k algorithmic flop
+        bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        peak = bf16 * (2 * d + 2 * k) / (6 * d + 12 * k)
+        bound, peak_note = "tensor", (f"{peaks['_source']} sustained bf16 {bf16:.0f} TFLOP/s x (2d+2k)/(6d+12k) "
+                                      "(split-precision fp32-equivalent)")
+    else:
+        peak = ffma_peak
+        bound, peak_note = "fp32", f"148 SMs x 128 FFMA lanes x 2 x {sm_max:.0f} MHz ({peaks['_source']} sm_max_mhz)"
+    roofline = {
+        "bound": bound,
+        "achieved": achieved,
+        "peak": peak,
+        "unit": "TFLOP/s",
+        "frac": achieved / peak,
+        "traffic": None,
+        "kernel": "kmm_tc_kernel" if layout == _lib.LAYOUT_TC else "kmm_simt_kernel",
+        "peak_note": peak_note,
+        "ffma_peak_tflops": ffma_peak,
+        "flops_per_entry": 2 * d + 2 * k,
+        "hbm_algorithmic_gb": 4 * (n * d + n * k + rows_per_rank * k) / 1e9,
+    }
+
+    line = {
+        "metric": "kernel_matmat_gentries_per_s",
+        "value": value,
+        "unit": "Gentries/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": _config(args.workload, kernel, n, d, k, world),
+        "clocks": clocks,
+        "e2e": {
+            "value": e2e_value,
+            "unit": "Gentries/s",
+            "h2d_bytes_per_step": X.numel() * 4 + V.numel() * 4,
+            "d2h_bytes_per_step": n * k * 4,
+            "steps": e2e_steps,
+        },
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "kernel_path": "tcgen05" if layout == _lib.LAYOUT_TC else "cuda-core",
+        "checksum_abs_sum": checksum,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        base = cpu_baseline(kernel, X, V, budget_s=args.ref_budget_s)
+        base.pop("seconds", None)
+        line["cpu_baseline"] = base
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--ref-budget-s", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,13 @@
+"""rlaopt_b200 — B200-native implicit kernel-matrix matmat behind the rlaopt API.
+
+``rlaopt_b200.kernels`` and ``rlaopt_b200.linops`` mirror ``rlaopt.kernels`` /
+``rlaopt.linops`` for the one hot path this package rebuilds:
+``Y = c * K(A1_rows, A2) @ V`` for RBF / Laplace / Matern kernels, evaluated by
+hand-written sm_100a CUDA kernels behind the C ABI of ``include/rlaopt_b200.h``.
+"""
+import torch  # noqa: F401  (device memory, streams, torch.distributed plumbing)
+
+from . import ops  # registers torch.ops.rlaopt_b200.kernel_matmat  # noqa: F401
+from . import linops, kernels  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,91 @@
+"""ctypes binding of the C ABI declared in ``include/rlaopt_b200.h``.
+
+The shared library ``rlaopt_b200/csrc/librlaopt_b200.so`` is built in-tree by
+``python -m rlaopt_b200.csrc.build`` (``__graft_entry__.build()``).  There is no
+CPU fallback: if the library is missing, or no CUDA device is usable, every
+compute entry raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "librlaopt_b200.so")
+
+LAYOUT_SIMT = 0
+LAYOUT_TC = 1
+
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/rlaopt_b200.h one to one
+_f32p, _f64p, _i64p = c_void_p, c_void_p, c_void_p
+PROTOTYPES = {
+    "rlaopt_b200_abi_version": (c_int, []),
+    "rlaopt_b200_last_error": (c_char_p, []),
+    "rlaopt_b200_device_sm_count": (c_int, []),
+    "rlaopt_b200_layout_supported": (c_int, [c_int, c_int, c_int64, c_int64, c_int]),
+    "rlaopt_b200_packed_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "rlaopt_b200_pack_points_f32": (
+        c_int,
+        [_f32p, c_int64, c_int64, c_int64, _i64p, c_float, _f32p, c_int, c_void_p, c_void_p],
+    ),
+    "rlaopt_b200_pack_points_f64": (
+        c_int,
+        [_f64p, c_int64, c_int64, c_int64, _i64p, c_double, _f64p, c_int, c_void_p, c_void_p],
+    ),
+    "rlaopt_b200_matmat_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int, c_int]),
+    "rlaopt_b200_matmat_packed_f32": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, _f32p, c_int64, c_int64, _f32p, c_int64, c_int, c_float,
+         c_int, c_void_p, c_size_t, c_void_p],
+    ),
+    "rlaopt_b200_matmat_packed_f64": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, _f64p, c_int64, c_int64, _f64p, c_int64, c_int, c_double,
+         c_int, c_void_p, c_size_t, c_void_p],
+    ),
+    "rlaopt_b200_kernel_matmat_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int, c_int]),
+    "rlaopt_b200_kernel_matmat_f32": (
+        c_int,
+        [_f32p, c_int64, c_int64, _f32p, c_int64, c_int64, c_int64, _f32p, c_int64, c_int64, _f32p, c_int64, c_int,
+         c_float, _f32p, c_float, c_int, _i64p, c_int64, _i64p, c_int64, c_int, c_void_p, c_size_t, c_void_p],
+    ),
+    "rlaopt_b200_kernel_matmat_f64": (
+        c_int,
+        [_f64p, c_int64, c_int64, _f64p, c_int64, c_int64, c_int64, _f64p, c_int64, c_int64, _f64p, c_int64, c_int,
+         c_double, _f64p, c_double, c_int, _i64p, c_int64, _i64p, c_int64, c_int, c_void_p, c_size_t, c_void_p],
+    ),
+    "rlaopt_b200_kernel_matmat_host_f32": (
+        c_int,
+        [_f32p, c_int64, _f32p, c_int64, c_int64, _f32p, c_int64, _f32p, c_int, c_float, c_float, c_int, c_int],
+    ),
+}
+
+
+def load():
+    """Load (once) and return the ctypes handle; raise loudly if the build is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"rlaopt_b200: CUDA extension not built ({LIB_PATH} missing). "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` or `python -m rlaopt_b200.csrc.build`. "
+            "There is no CPU fallback for the kernel-matmat path."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here means header and library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    """Turn a non-zero ABI return code into RuntimeError (reference ops raise via TORCH_CHECK)."""
+    if rc != 0:
+        msg = load().rlaopt_b200_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"rlaopt_b200.{what} failed (code {rc}): {msg}")

@@ -1,0 +1,134 @@
+"""One-process-per-GPU (SPMD) row-sharded operator over ``torch.distributed``.
+
+The reference's multi-device layer is host-side multiprocessing
+(``rlaopt/linops/base.py:114-291``); its only collective prototype is
+``experiments/distributed_matvec_v4.py:36-79`` (NCCL ``all_gather`` of per-rank
+partial results).  This is the production form of that prototype for launches
+under ``torchrun``: every rank owns the row block ``torch.chunk(arange(n), world)[rank]``
+of the operator (same partition as ``rlaopt/kernels/base.py:297-299``),
+
+    matvec  : local block product, then all-gather of the row blocks  (ROW mode, concat)
+    rmatvec : local partial product of the rank's rows, then all-reduce (ROW mode, sum)
+
+Backend-agnostic: NCCL over NVLink on GPUs, gloo on CPU for the tests.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .base import _BaseLinOp
+
+__all__ = ["RowShardedLinOp", "shard_rows"]
+
+
+def shard_rows(n: int, world: int) -> list[tuple[int, int]]:
+    """[lo, hi) row ranges per rank — ``torch.chunk(arange(n), world)`` without the tensor.
+
+    ``torch.chunk`` may produce fewer than ``world`` chunks; the remaining ranks own
+    an empty range.
+    """
+    size = -(-n // world)  # ceil
+    ranges = []
+    for r in range(world):
+        lo = min(r * size, n)
+        ranges.append((lo, min(lo + size, n)))
+    return ranges
+
+
+class RowShardedLinOp(_BaseLinOp):
+    """Global (n x m) operator whose rows are sharded over the ranks of a process group.
+
+    ``local_op`` is this rank's (n_r x m) block (``None`` for a rank that owns no
+    rows).  Inputs and outputs are replicated: every rank passes the same ``x`` and
+    receives the full result, which keeps the solvers' code unchanged.
+    """
+
+    def __init__(
+        self,
+        local_op: Optional[_BaseLinOp],
+        shape: torch.Size,
+        device: torch.device,
+        dtype: torch.dtype,
+        group: Optional[dist.ProcessGroup] = None,
+    ):
+        super().__init__(device=device, shape=shape, dtype=dtype)
+        if not dist.is_initialized():
+            raise RuntimeError("RowShardedLinOp needs an initialised torch.distributed process group")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.ranges = shard_rows(shape[0], self.world)
+        self.lo, self.hi = self.ranges[self.rank]
+        if local_op is None and self.hi > self.lo:
+            raise ValueError("this rank owns rows but has no local operator")
+        if local_op is not None and tuple(local_op.shape) != (self.hi - self.lo, shape[1]):
+            raise ValueError(f"local block has shape {tuple(local_op.shape)}, expected {(self.hi - self.lo, shape[1])}")
+        self.local_op = local_op
+        self._block = self.ranges[0][1] - self.ranges[0][0]  # largest block (padding size)
+
+    # -- local pieces (no communication) -----------------------------------
+    def local_matmat(self, x: torch.Tensor) -> torch.Tensor:
+        """This rank's rows of ``A @ x``."""
+        cols = 1 if x.ndim == 1 else x.shape[1]
+        if self.local_op is None:
+            return x.new_zeros((0,) if x.ndim == 1 else (0, cols))
+        return self.local_op @ x
+
+    # -- global products ---------------------------------------------------
+    def _gather_rows(self, local: torch.Tensor) -> torch.Tensor:
+        vec = local.ndim == 1
+        loc = local.unsqueeze(1) if vec else local
+        k = loc.shape[1]
+        if loc.shape[0] < self._block:
+            pad = loc.new_zeros((self._block - loc.shape[0], k))
+            loc = torch.cat([loc, pad], dim=0)
+        buf = loc.new_empty((self.world * self._block, k))
+        dist.all_gather_into_tensor(buf, loc.contiguous(), group=self.group)
+        n = self.shape[0]
+        if self.world * self._block != n:  # ragged tail: drop the padding rows
+            buf = torch.cat([buf[r * self._block : r * self._block + (hi - lo)] for r, (lo, hi) in enumerate(self.ranges)])
+        return buf[:, 0] if vec else buf
+
+    def _matvec(self, x: torch.Tensor) -> torch.Tensor:
+        return self._gather_rows(self.local_matmat(x))
+
+    def _matmat(self, x: torch.Tensor) -> torch.Tensor:
+        return self._matvec(x)
+
+    def _rmatvec(self, w: torch.Tensor) -> torch.Tensor:
+        m = self.shape[1]
+        if self.local_op is None:
+            part = w.new_zeros((m,) if w.ndim == 1 else (m, w.shape[1]))
+        else:
+            part = (self.local_op.T @ w[self.lo : self.hi]).contiguous()
+        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+        return part
+
+    def _rmatmat(self, w: torch.Tensor) -> torch.Tensor:
+        return self._rmatvec(w)
+
+    @property
+    def T(self):
+        outer = self
+
+        class _Adjoint(_BaseLinOp):
+            def _matvec(self, x):
+                return outer._rmatvec(x)
+
+            def _matmat(self, x):
+                return outer._rmatvec(x)
+
+            def _rmatvec(self, x):
+                return outer._matvec(x)
+
+            def _rmatmat(self, x):
+                return outer._matvec(x)
+
+            @property
+            def T(self):
+                return outer
+
+        return _Adjoint(self._device, torch.Size((self.shape[1], self.shape[0])), self._dtype)

@@ -1,0 +1,87 @@
+"""The C-ABI library loads and exports every symbol ``include/rlaopt_b200.h`` declares.
+
+No compute call is made (there is no GPU in the CPU tier); only pure-host entry
+points are invoked.
+"""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rlaopt_b200.h")
+
+
+def _declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rlaopt_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from rlaopt_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        from rlaopt_b200.csrc import build
+
+        build.build()
+    return _lib.load()
+
+
+def test_header_declares_expected_entry_points():
+    names = _declared_functions()
+    for required in (
+        "rlaopt_b200_abi_version",
+        "rlaopt_b200_pack_points_f32",
+        "rlaopt_b200_pack_points_f64",
+        "rlaopt_b200_matmat_packed_f32",
+        "rlaopt_b200_matmat_packed_f64",
+        "rlaopt_b200_kernel_matmat_f32",
+        "rlaopt_b200_kernel_matmat_f64",
+        "rlaopt_b200_kernel_matmat_host_f32",
+    ):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    raw = ctypes.CDLL(lib._name)
+    for name in _declared_functions():
+        assert hasattr(raw, name), f"{name} declared in the header but not exported"
+
+
+def test_python_prototypes_cover_the_header(lib):
+    from rlaopt_b200 import _lib
+
+    assert sorted(_lib.PROTOTYPES) == _declared_functions()
+
+
+def test_host_only_entry_points(lib):
+    from rlaopt_b200._lib import LAYOUT_SIMT, LAYOUT_TC
+
+    assert lib.rlaopt_b200_abi_version() == 1
+    # SIMT layout: rows padded to 128, features to 8
+    assert lib.rlaopt_b200_packed_bytes(10, 3, 4, LAYOUT_SIMT) == 128 * 8 * 4
+    assert lib.rlaopt_b200_packed_bytes(129, 9, 8, LAYOUT_SIMT) == 256 * 16 * 8
+    assert lib.rlaopt_b200_packed_bytes(0, 3, 4, LAYOUT_SIMT) == 0
+    # every kernel / dtype is supported on the CUDA-core layout
+    for kid in range(5):
+        for elem in (4, 8):
+            assert lib.rlaopt_b200_layout_supported(kid, elem, 3, 1, LAYOUT_SIMT) == 1
+    assert lib.rlaopt_b200_layout_supported(7, 4, 3, 1, LAYOUT_SIMT) == 0
+    # Laplace (L1) and fp64 never run on the tensor-core layout
+    assert lib.rlaopt_b200_layout_supported(1, 4, 128, 64, LAYOUT_TC) == 0
+    assert lib.rlaopt_b200_layout_supported(0, 8, 128, 64, LAYOUT_TC) == 0
+
+
+def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
+    from rlaopt_b200 import _lib
+
+    rc = lib.rlaopt_b200_matmat_packed_f32(None, 4, None, 4, 3, None, 1, 1, None, 1, 99, 1.0, 0, None, 0, None)
+    assert rc == -1
+    assert b"unknown kernel" in lib.rlaopt_b200_last_error()
+    rc = lib.rlaopt_b200_pack_points_f32(None, 4, 0, 0, None, 1.0, None, 0, None, None)
+    assert rc == -1
+    with pytest.raises(RuntimeError, match="code -1"):
+        _lib.check(rc, "pack_points")

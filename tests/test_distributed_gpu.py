@@ -1,0 +1,80 @@
+"""Multi-device kernel operator on real GPUs (single process, devices = {cuda:i}).
+
+Replays ``tests/kernels/test_distributed.py`` of the reference with CUDA devices
+only (the reference puts the CPU in the device set; this build has no CPU compute
+path — documented deviation).  Uses every visible GPU, so the same test
+covers 1 GPU (driver's round-end run) and 2+ GPUs (``gpurun --gpus 2``).
+"""
+import pytest
+import torch
+
+from oracle import kernel_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+
+def _devices():
+    return {torch.device("cuda", i) for i in range(min(torch.cuda.device_count(), 4))}
+
+
+@pytest.mark.parametrize("use_full_kernel", [True, False])
+def test_distributed_rbf_matches_oracle(use_full_kernel):
+    from rlaopt_b200.kernels import DistributedRBFLinOp, KernelConfig
+
+    g = torch.Generator().manual_seed(0)
+    n, m, d, k = 1031, 517, 9, 4
+    A1, A2 = torch.randn(n, d, generator=g), torch.randn(m, d, generator=g)
+    V, W = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g)
+    dev0 = torch.device("cuda:0")
+    devs = _devices()
+    op = DistributedRBFLinOp(A1.to(dev0), A2.to(dev0), KernelConfig(const_scaling=2.0, lengthscale=1.5), devices=devs,
+                             use_full_kernel=use_full_kernel)
+    try:
+        assert len(op.devices) == len(devs) and op.shape == (n, m)
+        blk = torch.randperm(n, generator=g)[:101]
+        blk = blk[blk < m]  # block oracle indexes both A1 and A2
+        ref_row = ko.kernel_matmat(A1, A2, V, "rbf", 1.5, 2.0, row_idx=blk, dtype=torch.float64)
+        got_row = op.row_oracle(blk) @ V.to(dev0)
+        assert got_row.device == dev0 and ko.rel_fro_error(got_row, ref_row) <= 1e-5
+        Vb = V[: blk.shape[0]]
+        ref_blk = ko.kernel_matmat(A1, A2, Vb, "rbf", 1.5, 2.0, row_idx=blk, col_idx=blk, dtype=torch.float64)
+        got_blk = op.blk_oracle(blk) @ Vb.to(dev0)
+        assert ko.rel_fro_error(got_blk, ref_blk) <= 1e-5
+        if use_full_kernel:
+            ref = ko.kernel_matmat(A1, A2, V, "rbf", 1.5, 2.0, dtype=torch.float64)
+            got = op @ V.to(dev0)
+            assert got.device == dev0 and ko.rel_fro_error(got, ref) <= 1e-5
+            assert ko.rel_fro_error(op @ V[:, 0].to(dev0), ref[:, 0]) <= 1e-5
+            ref_t = ko.kernel_matmat(A1, A2, W, "rbf", 1.5, 2.0, transpose=True, dtype=torch.float64)
+            assert ko.rel_fro_error(op.T @ W.to(dev0), ref_t) <= 1e-5
+            assert ko.rel_fro_error((W.T.to(dev0) @ op).T, ref_t) <= 1e-5
+        else:
+            with pytest.raises(RuntimeError):
+                op @ V.to(dev0)
+    finally:
+        op.shutdown()
+
+
+def test_distributed_symmetric_krr_operator_all_kernels():
+    import rlaopt_b200.kernels as kernels
+    from rlaopt_b200.kernels import KernelConfig
+
+    g = torch.Generator().manual_seed(1)
+    n, d, k = 2000, 16, 8
+    X = torch.randn(n, d, generator=g) / 4
+    V = torch.randn(n, k, generator=g)
+    dev0 = torch.device("cuda:0")
+    Xg = X.to(dev0)
+    for cls, name in (
+        (kernels.DistributedLaplaceLinOp, "laplace"),
+        (kernels.DistributedMatern12LinOp, "matern12"),
+        (kernels.DistributedMatern32LinOp, "matern32"),
+        (kernels.DistributedMatern52LinOp, "matern52"),
+    ):
+        ls = torch.linspace(0.5, 2.0, d)
+        op = cls(Xg, Xg, KernelConfig(lengthscale=ls.to(dev0)), devices=_devices())
+        try:
+            ref = ko.kernel_matmat(X, X, V, name, ls, dtype=torch.float64)
+            assert ko.rel_fro_error(op @ V.to(dev0), ref) <= 1e-5, name
+        finally:
+            op.shutdown()
