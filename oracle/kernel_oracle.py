@@ -169,6 +169,8 @@ def kernel_matmat_gemm_form(
     lengthscale: Lengthscale,
     const_scaling: float = 1.0,
     chunk: int = 2048,
+    row_idx: Optional[torch.Tensor] = None,
+    dtype: Optional[torch.dtype] = None,
 ) -> torch.Tensor:
     """Fastest honest CPU path for the L2 kernels: ``|x|^2 + |y|^2 - 2 x.y`` via GEMM.
 
@@ -179,7 +181,11 @@ def kernel_matmat_gemm_form(
     """
     name = _as_kernel_name(kernel)
     if name == "laplace":
-        return kernel_matmat(A1, A2, V, name, lengthscale, const_scaling)
+        return kernel_matmat(A1, A2, V, name, lengthscale, const_scaling, row_idx=row_idx, dtype=dtype)
+    if row_idx is not None:
+        A1 = A1[row_idx]
+    if dtype is not None:  # fp64: ground truth for large sampled-row checks (cancellation ~1e-15)
+        A1, A2, V = A1.to(dtype), A2.to(dtype), V.to(dtype)
     if isinstance(lengthscale, torch.Tensor):
         lengthscale = lengthscale.to(A1.dtype)
     X, Y = A1 / lengthscale, A2 / lengthscale

@@ -248,7 +248,7 @@ def test_size_independent_properties(dev):
 
 
 def test_full_size_c2_sampled_rows(dev):
-    """BASELINE configs[1]: RBF n = m = 1M, d = 128, k = 64 fp32; fp64 oracle on 128 sampled rows."""
+    """BASELINE configs[1]: RBF n = m = 1M, d = 128, k = 64 fp32; fp64 oracle on 512 sampled rows."""
     from rlaopt_b200.kernels import KernelConfig, RBFLinOp
 
     n, d, k = 1_000_000, 128, 64
@@ -259,8 +259,8 @@ def test_full_size_c2_sampled_rows(dev):
     op = RBFLinOp(Xg, Xg, KernelConfig(lengthscale=1.0))
     Y = op @ V.to(dev)
     assert Y.shape == (n, k)
-    rows = torch.randperm(n, generator=torch.Generator().manual_seed(1))[:128]
-    ref = ko.kernel_matmat(X, X, V, "rbf", 1.0, row_idx=rows, dtype=torch.float64, chunk=16)
+    rows = torch.randperm(n, generator=torch.Generator().manual_seed(1))[:512]
+    ref = ko.kernel_matmat_gemm_form(X, X, V, "rbf", 1.0, row_idx=rows, dtype=torch.float64, chunk=128)
     err = ko.rel_fro_error(Y[rows.to(dev)], ref)
     assert err <= 1e-5, f"C2 rel err {err:.3e}"
     # symmetric operator: K^T V == K V
