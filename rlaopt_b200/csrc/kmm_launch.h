@@ -35,6 +35,11 @@ size_t simt_workspace_bytes(int64_t n, int64_t m, int64_t k, int sm_count);
 template <typename T>
 cudaError_t launch_simt(const SimtArgs<T>& args, int sm_count, void* workspace, size_t workspace_bytes);
 
+// sum of per-split partial results [splits][n][k] -> Y (deterministic, fixed order)
+template <typename T>
+cudaError_t launch_split_reduce(const T* part, int splits, int64_t n, int64_t k, T* Y, int64_t ldy, T scale,
+                                cudaStream_t stream);
+
 // ---- tcgen05 tensor-core fused matmat for the L2 kernels, fp32 in/out (kmm_tc.cu) ----
 bool tc_supported_d(int64_t d);
 bool tc_supported_k(int64_t k);

@@ -298,6 +298,19 @@ cudaError_t launch_kc(const SimtArgs<T>& a, int kc, int splits, int tiles_per_sp
 }  // namespace
 
 template <typename T>
+cudaError_t launch_split_reduce(const T* part, int splits, int64_t n, int64_t k, T* Y, int64_t ldy, T scale,
+                                cudaStream_t stream) {
+    const int64_t nk = n * k;
+    const int threads = 256;
+    kmm_split_reduce_kernel<T><<<(unsigned)((nk + threads - 1) / threads), threads, 0, stream>>>(part, splits, nk, k, Y,
+                                                                                                ldy, scale);
+    return cudaGetLastError();
+}
+template cudaError_t launch_split_reduce<float>(const float*, int, int64_t, int64_t, float*, int64_t, float, cudaStream_t);
+template cudaError_t launch_split_reduce<double>(const double*, int, int64_t, int64_t, double*, int64_t, double,
+                                                 cudaStream_t);
+
+template <typename T>
 int simt_pick_kc(int64_t k) {
     const int kc_max = sizeof(T) == 4 ? 64 : 32;
     int kc = 8;

@@ -73,6 +73,11 @@ def choose_layout(kid: int, dtype: torch.dtype, d: int, k: int) -> int:
         return LAYOUT_SIMT
     elem = 4 if dtype == torch.float32 else 8
     tc_ok = bool(_lib.load().rlaopt_b200_layout_supported(kid, elem, d, k, LAYOUT_TC))
+    if kid == KERNEL_IDS["matern12"] and forced != "tc":
+        # exp(-r) is not smooth at r = 0: the GEMM-form distance |x|^2+|y|^2-2x.y leaves an
+        # O(sqrt(eps)) error on (near-)coincident points, so Matern-1/2 stays on the
+        # direct-difference CUDA-core kernel (SURVEY §7 "hard parts").
+        tc_ok = False
     if forced == "tc":
         if not tc_ok:
             raise RuntimeError(f"RLAOPT_B200_LAYOUT=tc but kernel={_KERNEL_NAMES[kid]} dtype={dtype} d={d} k={k} unsupported")
@@ -125,7 +130,7 @@ def pack_points(
         ldx = X.stride(0) if X.shape[0] > 1 else max(d, 1)
         rc = fn(_ptr(X), n, d, ldx, _ptr(idx), inv, _ptr(inv_vec), layout, _ptr(buf), _stream(X.device))
         _lib.check(rc, "pack_points")
-    LAUNCH_COUNT += 1
+    LAUNCH_COUNT += 2 if layout == LAYOUT_TC else 1  # TC: abs-max + split/pack kernels
     return PackedPoints(buf, n, d, X.dtype, layout)
 
 
@@ -170,7 +175,11 @@ def matmat_packed(
             float(const_scaling), rows.layout, _ptr(ws), ws_bytes, _stream(V.device),
         )
         _lib.check(rc, "matmat_packed")
-    LAUNCH_COUNT += 2 if ws_bytes else 1
+    if rows.layout == LAYOUT_TC:  # V split/pack + fused kernel (+ split reduce)
+        v_bytes = -(-cols.n // 64) * (-(-k // 16) * 16) * 512
+        LAUNCH_COUNT += 3 if ws_bytes > 2 * v_bytes else 2
+    else:
+        LAUNCH_COUNT += 2 if ws_bytes else 1
     return Y[:, 0] if vec else Y
 
 

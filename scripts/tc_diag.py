@@ -1,0 +1,67 @@
+"""Diagnostic sweep of the tcgen05 path against the fp64 oracle (run on the GPU box)."""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import kernel_oracle as ko  # noqa: E402
+from rlaopt_b200 import _lib, ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+
+
+def rnd(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+def run(name, n, m, d, k, layout, scale=1.0, ls=1.0):
+    A1 = rnd((n, d), 1) / d**0.5 * scale
+    A2 = rnd((m, d), 2) / d**0.5 * scale
+    V = rnd((m, k), 3)
+    ref = ko.kernel_matmat_gemm_form(A1, A2, V, name, ls, dtype=torch.float64) if name != "laplace" else ko.kernel_matmat(A1, A2, V, name, ls, dtype=torch.float64)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    got = ops.kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), name, ls, layout=layout)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    err = ko.rel_fro_error(got, ref)
+    print(f"{name:9s} n={n:6d} m={m:6d} d={d:3d} k={k:3d} layout={layout} rel_err={err:.3e} max_abs_ref={ref.abs().max():.3e} t={dt*1e3:.1f}ms", flush=True)
+    return got, ref
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "basic"
+    TC = _lib.LAYOUT_TC
+    if which == "basic":
+        # K readout with V = identity: errors are per-entry
+        n = m = 64
+        A = rnd((n, 16), 5) / 4
+        I = torch.eye(m)
+        Kref = ko.kernel_matrix(A, A, "rbf", 1.0, dtype=torch.float64)
+        Kg = ops.kernel_matmat(A.to(dev), A.to(dev), I.to(dev), "rbf", 1.0, layout=TC).cpu().double()
+        print("K readout 64x64 d=16: max abs err", (Kg - Kref).abs().max().item(), "diag", Kg.diagonal()[:4].tolist(), flush=True)
+        if (Kg - Kref).abs().max().item() > 1e-3:
+            print("Kg[:4,:4]\n", Kg[:4, :4], "\nKref[:4,:4]\n", Kref[:4, :4], flush=True)
+        for args in [
+            ("rbf", 128, 64, 16, 16),
+            ("rbf", 128, 64, 64, 64),
+            ("rbf", 128, 128, 128, 64),
+            ("rbf", 100, 300, 3, 1),
+            ("rbf", 1000, 2000, 128, 64),
+            ("matern32", 1000, 2000, 32, 16),
+            ("matern52", 1000, 2000, 32, 16),
+            ("matern12", 1000, 2000, 32, 16),
+            ("rbf", 300, 5000, 100, 130),
+            ("rbf", 300, 5000, 192, 64),
+            ("rbf", 70, 40000, 50, 7),
+            ("rbf", 8192, 8192, 128, 64),
+        ]:
+            run(*args, TC)
+        run("rbf", 8192, 8192, 128, 64, _lib.LAYOUT_SIMT)
+    elif which == "big":
+        for args in [("rbf", 32768, 32768, 128, 64), ("matern52", 32768, 32768, 32, 16), ("rbf", 65536, 65536, 128, 64)]:
+            run(*args, TC)
+            run(*args, TC)
