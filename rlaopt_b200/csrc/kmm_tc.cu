@@ -21,6 +21,7 @@
 //   P   = hi + lo (+2^-21), tf32 pair;  V likewise
 // K is never written to HBM; S and P never leave TMEM / registers.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "kmm_common.cuh"
 #include "kmm_launch.h"
@@ -279,7 +280,7 @@ struct TcParams {
     float* out;
     int64_t ldo, split_stride;
     int64_t n, m;
-    int k, kb, nk1, stages, kid;
+    int k, kb, nk1, stages, kid, period;
     float scale_out;
     int64_t sub_tiles;        // ceil(m / 64)
     int tiles_per_split;
@@ -409,14 +410,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
                     umma_commit(&s_full[b1]);
                 }
                 const int s = (int)(u % STAGES), b = (int)(u & 1);
-                const int in_period = (int)(u % TC_PERIOD);
+                const int in_period = (int)(u % p.period);
                 mbar_wait(&p_full[b], (uint32_t)((u >> 1) & 1));
-                if (in_period == 0) mbar_wait(o_free, (uint32_t)(((u / TC_PERIOD) & 1) ^ 1));
+                if (in_period == 0) mbar_wait(o_free, (uint32_t)(((u / p.period) & 1) ^ 1));
                 tc_fence_after();
                 issue_mma2(b, s, in_period != 0);
                 umma_commit(&empty[s]);
                 umma_commit(&p_free[b]);
-                if (in_period == TC_PERIOD - 1 || u == T - 1) umma_commit(o_full);
+                if (in_period == p.period - 1 || u == T - 1) umma_commit(o_full);
             }
         }
     } else {
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         for (int c = 0; c < KP / 2; ++c) acc[c] = 0.0f;
 
         auto drain = [&](int64_t u) {
-            mbar_wait(o_full, (uint32_t)((u / TC_PERIOD) & 1));
+            mbar_wait(o_full, (uint32_t)((u / p.period) & 1));
             tc_fence_after();
 #pragma unroll
             for (int g = 0; g < KP / 16; ++g) {
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[b]);
-            if ((u % TC_PERIOD) == TC_PERIOD - 1 || u == T - 1) drain(u);
+            if ((u % p.period) == p.period - 1 || u == T - 1) drain(u);
         }
 
         // ---- write this thread's half row of Y ----
@@ -635,6 +636,11 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     p.nk1 = (int)((d + 15) / 16);
     p.stages = pl.stages;
     p.kid = kid;
+    p.period = TC_PERIOD;
+    if (const char* env = getenv("RLAOPT_B200_TC_PERIOD")) {  // experiment knob: drain interval of the O accumulator
+        const int v = atoi(env);
+        if (v >= 1 && v <= 1024) p.period = v;
+    }
     p.sub_tiles = pl.sub_tiles;
     p.tiles_per_split = pl.tiles_per_split;
     if (pl.splits > 1) {

@@ -65,3 +65,50 @@ if __name__ == "__main__":
         for args in [("rbf", 32768, 32768, 128, 64), ("matern52", 32768, 32768, 32, 16), ("rbf", 65536, 65536, 128, 64)]:
             run(*args, TC)
             run(*args, TC)
+    elif which == "period":
+        for per in ("1", "2", "4", "8", "16", "64"):
+            os.environ["RLAOPT_B200_TC_PERIOD"] = per
+            print("PERIOD", per, flush=True)
+            run("rbf", 2048, 16384, 128, 64, TC)
+            run("matern52", 2048, 16384, 32, 16, TC)
+        os.environ.pop("RLAOPT_B200_TC_PERIOD")
+        # all-positive V (coherent sums): bias shows up as a relative offset
+        A = rnd((2048, 128), 1) / 128**0.5
+        B = rnd((16384, 128), 2) / 128**0.5
+        V = rnd((16384, 64), 3).abs()
+        ref = ko.kernel_matmat_gemm_form(A, B, V, "rbf", 1.0, dtype=torch.float64)
+        for per in ("1", "4", "16"):
+            os.environ["RLAOPT_B200_TC_PERIOD"] = per
+            got = ops.kernel_matmat(A.to(dev), B.to(dev), V.to(dev), "rbf", 1.0, layout=TC).cpu().double()
+            rel = ((got - ref) / ref)
+            print(f"positive V period {per}: mean rel {rel.mean().item():.3e} rms {rel.pow(2).mean().sqrt().item():.3e}", flush=True)
+    elif which == "perf":
+        from rlaopt_b200.kernels import KernelConfig, RBFLinOp, Matern52LinOp
+        for per in ("16", "4", "1"):
+            os.environ["RLAOPT_B200_TC_PERIOD"] = per
+            for cls, n, d, k in ((RBFLinOp, 131072, 128, 64), (Matern52LinOp, 262144, 32, 16)):
+                X = (rnd((n, d), 1) / d**0.5).to(dev)
+                V = rnd((n, k), 2).to(dev)
+                op = cls(X, X, KernelConfig(lengthscale=1.0))
+                for _ in range(2):
+                    Y = op @ V
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    Y = op @ V
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 3
+                print(f"period {per} {cls.__name__} n={n} d={d} k={k}: {ms:.2f} ms  {n*n/ms/1e6:.1f} Gentries/s", flush=True)
+    elif which == "prof":
+        from rlaopt_b200.kernels import KernelConfig, RBFLinOp
+        n, m, d, k = 148 * 128, 65536, 128, 64
+        X1 = (rnd((n, d), 1) / d**0.5).to(dev)
+        X2 = (rnd((m, d), 2) / d**0.5).to(dev)
+        V = rnd((m, k), 3).to(dev)
+        op = RBFLinOp(X1, X2, KernelConfig(lengthscale=1.0))
+        for _ in range(3):
+            Y = op @ V
+        torch.cuda.synchronize()
+        print("done", float(Y.abs().sum()))
