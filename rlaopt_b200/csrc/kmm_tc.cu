@@ -12,9 +12,10 @@
 //                                        3 products hi.lo + lo.hi + hi.hi
 //   8 epilogue warps  tcgen05.ld S -> D = |x|^2+|y|^2-2S -> P = f(D) in registers
 //                   -> split P into tf32 hi/lo -> tcgen05.st back into TMEM;
-//                   every 16 sub-tiles drain O from TMEM into fp32 registers (round-to-
-//                   nearest adds, so the long column sum does not inherit the tensor
-//                   core's accumulator rounding)
+//                   -> drain the previous sub-tile's O from TMEM into fp32 registers: each
+//                   sub-tile gets a fresh TMEM accumulator and the long column sum is done
+//                   with round-to-nearest FADDs (the tensor core accumulates with
+//                   truncation, measured bias -1e-5 over 1024 columns)
 //
 // Split-precision arithmetic (why fp32 parity holds, DESIGN.md "numerics"):
 //   x*s = hi + lo (+2^-22), fp16 pair, s a power of two chosen per operand so |x*s| < 2^13
@@ -34,7 +35,7 @@ constexpr int TC_BM = 128;      // rows per CTA (TMEM lanes)
 constexpr int TC_BN = 64;       // K columns per sub-tile
 constexpr int TC_EPI_WARPS = 8; // warps 0..7: pointwise; warp 8: producer; warp 9: MMA issue
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
-constexpr int TC_PERIOD = 16;   // sub-tiles between drains of the O accumulator (1024 columns)
+constexpr int TC_MIN_SPLIT_TILES = 16;  // a column split covers at least 16 sub-tiles (1024 columns)
 constexpr int TC_KBLOCK_BYTES = 64 * 128;  // one K-block of a 64-row image: 64 rows x 128 B
 constexpr int TC_HEADER_BYTES = 256;
 constexpr int TC_MAX_D = 192;
@@ -79,12 +80,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps after ~4 s instead of hanging the GPU.
+// Bounded wait: try_wait suspends the thread in hardware for a while before it returns false,
+// so the counter only trips on a genuine protocol bug (trap instead of hanging the GPU).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000LL) __trap();
+        if (++spins > (1u << 24)) __trap();
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -280,12 +281,60 @@ struct TcParams {
     float* out;
     int64_t ldo, split_stride;
     int64_t n, m;
-    int k, kb, nk1, stages, kid, period;
+    int k, kb, nk1, stages, kid;
     float scale_out;
     int64_t sub_tiles;        // ceil(m / 64)
     int tiles_per_split;
 };
 
+// one elected lane of a converged warp (same lane every time for a full mask)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// tcgen05.mma with the shared-memory descriptor passed as (lo, hi) words: only the low word
+// (start address) changes between K steps, so advancing an operand is one 32-bit add.
+template <int FMT>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi,
+                                        uint32_t idesc, uint32_t acc) {
+    if constexpr (FMT == FMT_F16) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .b64 bd;\n"
+            "mov.b64 bd, {%2, %3};\n"
+            "setp.ne.b32 p, %5, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n"
+            "}\n" ::"r"(d_tmem),
+            "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .b64 bd;\n"
+            "mov.b64 bd, {%2, %3};\n"
+            "setp.ne.b32 p, %5, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n"
+            "}\n" ::"r"(d_tmem),
+            "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
+            : "memory");
+    }
+}
+
+// TMEM column map (512 columns x 128 lanes, fp32 words):
+//   [0, 32 KB)              X tile, fp16 hi halves (2 per column)
+//   [32 KB, 64 KB)          X tile, fp16 lo halves
+//   [64 KB, +256)           two S/P buffers: S (64 cols, overwritten in place by P_hi) | P_lo (64 cols)
+//   [64 KB + 256, +2 KP)    two O buffers (one fresh accumulator per sub-tile, alternating)
 template <int KP>
 __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -296,21 +345,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
     const uint32_t stage_bytes = a_img_bytes + v_img_bytes;
     float* ny_smem = reinterpret_cast<float*>(smem + (size_t)STAGES * stage_bytes);  // [STAGES][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ny_smem + STAGES * TC_BN);
-    uint64_t* full = bars;             // [STAGES] producer -> MMA / epilogue
-    uint64_t* empty = full + STAGES;   // [STAGES] MMA -> producer
-    uint64_t* s_full = empty + STAGES; // [2] MMA1 done
-    uint64_t* p_full = s_full + 2;     // [2] P written (8 warps)
-    uint64_t* p_free = p_full + 2;     // [2] MMA2 done reading P
-    uint64_t* o_full = p_free + 2;     // [1] O accumulator complete for this period
-    uint64_t* o_free = o_full + 1;     // [1] O drained (8 warps)
-    uint64_t* a_full = o_free + 1;     // [1] X tile resident in TMEM (8 warps)
+    uint64_t* full = bars;              // [STAGES] producer -> MMA / epilogue
+    uint64_t* empty = full + STAGES;    // [STAGES] MMA -> producer
+    uint64_t* s_full = empty + STAGES;  // [2] MMA1 done
+    uint64_t* p_full = s_full + 2;      // [2] P written (8 warps)
+    uint64_t* p_free = p_full + 2;      // [2] MMA2 done reading P
+    uint64_t* o_full = p_free + 2;      // [2] O buffer complete
+    uint64_t* o_free = o_full + 2;      // [2] O buffer drained (8 warps)
+    uint64_t* a_full = o_free + 2;      // [1] X tile resident in TMEM (8 warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
 
     const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
     const int kc = blockIdx.y;
     const int64_t t_begin = (int64_t)blockIdx.z * p.tiles_per_split;
     const int64_t t_end = min(p.sub_tiles, t_begin + (int64_t)p.tiles_per_split);
-    const int64_t T = t_end - t_begin;
+    const int T = (int)(t_end - t_begin);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -321,9 +370,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             mbar_init(&s_full[b], 1);
             mbar_init(&p_full[b], TC_EPI_WARPS);
             mbar_init(&p_free[b], 1);
+            mbar_init(&o_full[b], 1);
+            mbar_init(&o_free[b], TC_EPI_WARPS);
         }
-        mbar_init(o_full, 1);
-        mbar_init(o_free, TC_EPI_WARPS);
         mbar_init(a_full, TC_EPI_WARPS);
         fence_barrier_init();
     }
@@ -342,83 +391,138 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
     if (warp == TC_EPI_WARPS) {
         // =============================== producer ===============================
         if (lane == 0) {
-            const unsigned char* vbase = p.vimg + (size_t)kc * p.sub_tiles * v_img_bytes;
-            for (int64_t u = 0; u < T; ++u) {
-                const int s = (int)(u % STAGES);
-                mbar_wait(&empty[s], (uint32_t)(((u / STAGES) & 1) ^ 1));
-                const int64_t t = t_begin + u;
+            const unsigned char* a_src = col_images + (size_t)t_begin * a_img_bytes;
+            const unsigned char* v_src = p.vimg + ((size_t)kc * p.sub_tiles + t_begin) * v_img_bytes;
+            const float* n_src = col_norms + t_begin * TC_BN;
+            int s = 0;
+            uint32_t ph = 1;  // a fresh barrier passes a wait on parity 1
+            for (int u = 0; u < T; ++u) {
+                mbar_wait(&empty[s], ph);
                 unsigned char* dst = smem + (size_t)s * stage_bytes;
                 mbar_arrive_expect_tx(&full[s], stage_bytes + TC_BN * 4);
-                bulk_copy_g2s(dst, col_images + (size_t)t * a_img_bytes, a_img_bytes, &full[s]);
-                bulk_copy_g2s(dst + a_img_bytes, vbase + (size_t)t * v_img_bytes, v_img_bytes, &full[s]);
-                bulk_copy_g2s(ny_smem + s * TC_BN, col_norms + t * TC_BN, TC_BN * 4, &full[s]);
+                bulk_copy_g2s(dst, a_src, a_img_bytes, &full[s]);
+                bulk_copy_g2s(dst + a_img_bytes, v_src, v_img_bytes, &full[s]);
+                bulk_copy_g2s(ny_smem + s * TC_BN, n_src, TC_BN * 4, &full[s]);
+                a_src += a_img_bytes;
+                v_src += v_img_bytes;
+                n_src += TC_BN;
+                if (++s == STAGES) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
         }
     } else if (warp == TC_EPI_WARPS + 1) {
         // =============================== MMA issue ===============================
-        if (lane == 0) {
-            constexpr uint32_t idesc1 = umma_idesc(FMT_F16, TC_BN);
-            constexpr uint32_t idesc2 = umma_idesc(FMT_TF32, KP);
-            const int nk1 = p.nk1;  // K = 16 fp16 per instruction; d zero-padded to a multiple of 16
-            auto issue_mma1 = [&](int b, int s) {
-                const uint32_t d_t = tmem + col_sp + b * 128;
-                const uint32_t img = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t img_hi = img, img_lo = img + KB * TC_KBLOCK_BYTES;
+        // The whole warp runs the (warp-uniform) control flow so addresses live in uniform
+        // registers; one elected lane issues the tcgen05 instructions.
+        constexpr uint32_t idesc1 = umma_idesc(FMT_F16, TC_BN);
+        constexpr uint32_t idesc2 = umma_idesc(FMT_TF32, KP);
+        const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
+        const uint32_t desc_lo0 = (uint32_t)(umma_desc_sw128(0) & 0xFFFFFFFFu);
+        const int nk1 = p.nk1;
+        const uint32_t smem_base = smem_u32(smem);
+        const uint32_t lo_off = (uint32_t)KB * TC_KBLOCK_BYTES;
+
+        // S[b] = X . Y_tile^T : hi.lo + lo.hi + hi.hi, one K = 16 step per instruction
+        auto issue_mma1 = [&](int b, int s) {
+            const uint32_t d_t = tmem + col_sp + b * 128;
+            const uint32_t img = smem_base + (uint32_t)s * stage_bytes;
+            const uint32_t dlo_hi = desc_lo0 + (img >> 4);             // Y hi image
+            const uint32_t dlo_lo = desc_lo0 + ((img + lo_off) >> 4);  // Y lo image
+            if (elect_one()) {
                 uint32_t acc = 0;
-                // small terms first: hi.lo, lo.hi, then hi.hi
+#pragma unroll 1
                 for (int part = 0; part < 3; ++part) {
-                    const uint32_t a_col = tmem + (part == 1 ? col_a_lo : col_a_hi);
-                    const uint32_t b_img = (part == 0 ? img_lo : img_hi);
-                    for (int ks = 0; ks < nk1; ++ks) {
-                        const uint64_t bd = umma_desc_sw128(b_img + (ks >> 2) * TC_KBLOCK_BYTES + (ks & 3) * 32);
-                        umma_f16_ts(d_t, a_col + ks * 8, bd, idesc1, acc);
+                    uint32_t a = tmem + (part == 1 ? col_a_lo : col_a_hi);
+                    uint32_t bd = (part == 0 ? dlo_lo : dlo_hi);
+                    int ks = 0;
+#pragma unroll 1
+                    for (; ks + 4 <= nk1; ks += 4) {  // one 64-wide K-block: 4 steps of 32 B inside the 128 B row
+                        umma_ts<FMT_F16>(d_t, a, bd, desc_hi, idesc1, acc);
+                        umma_ts<FMT_F16>(d_t, a + 8, bd + 2, desc_hi, idesc1, 1);
+                        umma_ts<FMT_F16>(d_t, a + 16, bd + 4, desc_hi, idesc1, 1);
+                        umma_ts<FMT_F16>(d_t, a + 24, bd + 6, desc_hi, idesc1, 1);
                         acc = 1;
+                        a += 32;
+                        bd += TC_KBLOCK_BYTES >> 4;
+                    }
+                    for (; ks < nk1; ++ks) {
+                        umma_ts<FMT_F16>(d_t, a, bd, desc_hi, idesc1, acc);
+                        acc = 1;
+                        a += 8;
+                        bd += 2;
                     }
                 }
-            };
-            auto issue_mma2 = [&](int b, int s, uint32_t acc) {
-                const uint32_t d_t = tmem + col_o;
-                const uint32_t p_hi = tmem + col_sp + b * 128, p_lo = p_hi + 64;
-                const uint32_t img = smem_u32(smem + (size_t)s * stage_bytes + a_img_bytes);
-                const uint32_t v_hi = img, v_lo = img + KP * 256;
+            }
+            __syncwarp();
+        };
+        // O[b] = P[b] . V_tile : fresh accumulator per sub-tile, K = 8 (tf32) per instruction
+        auto issue_mma2 = [&](int b, int s) {
+            const uint32_t d_t = tmem + col_o + b * KP;
+            const uint32_t p_hi = tmem + col_sp + b * 128, p_lo = p_hi + 64;
+            const uint32_t img = smem_base + (uint32_t)s * stage_bytes + a_img_bytes;
+            const uint32_t dlo_hi = desc_lo0 + (img >> 4);
+            const uint32_t dlo_lo = desc_lo0 + ((img + KP * 256) >> 4);
+            if (elect_one()) {
+#pragma unroll
                 for (int part = 0; part < 3; ++part) {
-                    const uint32_t a_col = (part == 1 ? p_lo : p_hi);
-                    const uint32_t b_img = (part == 0 ? v_lo : v_hi);
+                    const uint32_t a = (part == 1 ? p_lo : p_hi);
+                    const uint32_t bd = (part == 0 ? dlo_lo : dlo_hi);
 #pragma unroll
                     for (int ks = 0; ks < TC_BN / 8; ++ks) {
-                        const uint64_t bd = umma_desc_sw128(b_img + (ks >> 2) * (KP * 128) + (ks & 3) * 32);
-                        umma_tf32_ts(d_t, a_col + ks * 8, bd, idesc2, acc);
-                        acc = 1;
+                        umma_ts<FMT_TF32>(d_t, a + ks * 8, bd + (ks >> 2) * ((KP * 128) >> 4) + (ks & 3) * 2, desc_hi,
+                                          idesc2, (part | ks) != 0);
                     }
                 }
-            };
-            mbar_wait(a_full, 0);
-            if (T > 0) {
-                mbar_wait(&full[0], 0);
-                tc_fence_after();
-                issue_mma1(0, 0);
-                umma_commit(&s_full[0]);
             }
-            for (int64_t u = 0; u < T; ++u) {
-                if (u + 1 < T) {
-                    const int64_t u1 = u + 1;
-                    const int s1 = (int)(u1 % STAGES), b1 = (int)(u1 & 1);
-                    mbar_wait(&full[s1], (uint32_t)((u1 / STAGES) & 1));
-                    mbar_wait(&p_free[b1], (uint32_t)(((u1 >> 1) & 1) ^ 1));
-                    tc_fence_after();
-                    issue_mma1(b1, s1);
-                    umma_commit(&s_full[b1]);
+            __syncwarp();
+        };
+        auto commit = [&](uint64_t* bar) {
+            if (elect_one()) umma_commit(bar);
+            __syncwarp();
+        };
+
+        mbar_wait(a_full, 0);
+        int s1 = 0, s2 = 0;        // ring slots of the tiles MMA1 / MMA2 work on
+        uint32_t ph1 = 0;          // parity of full[s1]
+        if (T > 0) {
+            mbar_wait(&full[0], 0);
+            tc_fence_after();
+            issue_mma1(0, 0);
+            commit(&s_full[0]);
+            if (++s1 == STAGES) {
+                s1 = 0;
+                ph1 ^= 1;
+            }
+        }
+        for (int u = 0; u < T; ++u) {
+            const int b = u & 1;
+            const uint32_t par = (uint32_t)((u >> 1) & 1);  // use count parity of buffer b
+            if (u + 1 < T) {
+                const int b1 = b ^ 1;
+                const uint32_t par1 = (uint32_t)(((u + 1) >> 1) & 1);
+                mbar_wait(&full[s1], ph1);
+                mbar_wait(&p_free[b1], par1 ^ 1);  // MMA2 of tile u-1 has consumed P[b1]
+                tc_fence_after();
+                issue_mma1(b1, s1);
+                commit(&s_full[b1]);
+                if (++s1 == STAGES) {
+                    s1 = 0;
+                    ph1 ^= 1;
                 }
-                const int s = (int)(u % STAGES), b = (int)(u & 1);
-                const int in_period = (int)(u % p.period);
-                mbar_wait(&p_full[b], (uint32_t)((u >> 1) & 1));
-                if (in_period == 0) mbar_wait(o_free, (uint32_t)(((u / p.period) & 1) ^ 1));
-                tc_fence_after();
-                issue_mma2(b, s, in_period != 0);
-                umma_commit(&empty[s]);
-                umma_commit(&p_free[b]);
-                if (in_period == p.period - 1 || u == T - 1) umma_commit(o_full);
             }
+            mbar_wait(&p_full[b], par);
+            mbar_wait(&o_free[b], par ^ 1);  // O[b] of tile u-2 has been drained
+            tc_fence_after();
+            issue_mma2(b, s2);
+            if (elect_one()) {
+                umma_commit(&empty[s2]);
+                umma_commit(&p_free[b]);
+                umma_commit(&o_full[b]);
+            }
+            __syncwarp();
+            if (++s2 == STAGES) s2 = 0;
         }
     } else {
         // =============================== epilogue warps ===============================
@@ -458,26 +562,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
 #pragma unroll
         for (int c = 0; c < KP / 2; ++c) acc[c] = 0.0f;
 
-        auto drain = [&](int64_t u) {
-            mbar_wait(o_full, (uint32_t)((u / p.period) & 1));
+        // fp32 round-to-nearest accumulation of one sub-tile's O buffer into registers
+        auto drain = [&](int b, uint32_t par) {
+            mbar_wait(&o_full[b], par);
             tc_fence_after();
 #pragma unroll
             for (int g = 0; g < KP / 16; ++g) {
                 uint32_t o[8];
-                tmem_ld8(tmem + lane_bits + col_o + h * (KP / 2) + g * 8, o);
+                tmem_ld8(tmem + lane_bits + col_o + b * KP + h * (KP / 2) + g * 8, o);
                 tmem_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 8; ++e) acc[g * 8 + e] += __uint_as_float(o[e]);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(o_free);
+            if (lane == 0) mbar_arrive(&o_free[b]);
         };
 
-        for (int64_t u = 0; u < T; ++u) {
-            const int s = (int)(u % STAGES), b = (int)(u & 1);
-            mbar_wait(&full[s], (uint32_t)((u / STAGES) & 1));  // |y|^2 of this sub-tile is in smem
-            mbar_wait(&s_full[b], (uint32_t)((u >> 1) & 1));
+        int s = 0;
+        uint32_t phs = 0;
+        for (int u = 0; u < T; ++u) {
+            const int b = u & 1;
+            const uint32_t par = (uint32_t)((u >> 1) & 1);
+            mbar_wait(&full[s], phs);  // |y|^2 of this sub-tile is in smem
+            mbar_wait(&s_full[b], par);
             tc_fence_after();
             const uint32_t t_s = tmem + lane_bits + col_sp + b * 128 + h * 32;
             uint32_t sv[32];
@@ -509,8 +617,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[b]);
-            if ((u % p.period) == p.period - 1 || u == T - 1) drain(u);
+            // drain the previous sub-tile's O while the tensor core works on this one
+            if (u > 0) drain(b ^ 1, (uint32_t)(((u - 1) >> 1) & 1));
+            if (++s == STAGES) {
+                s = 0;
+                phs ^= 1;
+            }
         }
+        if (T > 0) drain((T - 1) & 1, (uint32_t)(((T - 1) >> 1) & 1));
 
         // ---- write this thread's half row of Y ----
         if (grow < p.n) {
@@ -537,7 +651,7 @@ struct TcPlan {
 bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* pl) {
     if (d < 1 || d > TC_MAX_D || n < 1 || m < 1 || k < 1) return false;
     const int kb = tc_kblocks(d);
-    const int kp_max = kb <= 2 ? 128 : 64;  // TMEM: 64*KB + 256 + KP <= 512
+    const int kp_max = kb <= 2 ? 64 : 32;  // TMEM columns: 64*KB (X) + 256 (S/P x2) + 2*KP (O x2) <= 512
     int kp = 16;
     while (kp < kp_max && kp < k) kp *= 2;
     const size_t stage = tc_image_bytes(kb) + (size_t)kp * 512;
@@ -556,7 +670,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     int64_t splits = 1;
     if (base < target) {
         splits = (target + base - 1) / base;
-        const int64_t max_splits = (pl->sub_tiles + TC_PERIOD - 1) / TC_PERIOD;  // >= 1024 columns per split
+        const int64_t max_splits = (pl->sub_tiles + TC_MIN_SPLIT_TILES - 1) / TC_MIN_SPLIT_TILES;
         if (splits > max_splits) splits = max_splits;
         if (splits < 1) splits = 1;
     }
@@ -636,11 +750,6 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     p.nk1 = (int)((d + 15) / 16);
     p.stages = pl.stages;
     p.kid = kid;
-    p.period = TC_PERIOD;
-    if (const char* env = getenv("RLAOPT_B200_TC_PERIOD")) {  // experiment knob: drain interval of the O accumulator
-        const int v = atoi(env);
-        if (v >= 1 && v <= 1024) p.period = v;
-    }
     p.sub_tiles = pl.sub_tiles;
     p.tiles_per_split = pl.tiles_per_split;
     if (pl.splits > 1) {

@@ -199,12 +199,18 @@ def test_identical_points_and_large_distances(dev):
     """K(x, x) = 1 exactly on the diagonal; far-apart points underflow to 0 without NaN."""
     from rlaopt_b200.ops import kernel_matmat
 
+    from rlaopt_b200._lib import LAYOUT_SIMT
+
     A = _rand((64, 5), torch.float32, 9).to(dev)
     I = torch.eye(64, device=dev)
     for name in KERNELS:
-        Kd = kernel_matmat(A, A, I, name, 1.0)
+        # direct-difference CUDA-core kernel: the diagonal is exactly 1 and K is exactly symmetric
+        Kd = kernel_matmat(A, A, I, name, 1.0, layout=LAYOUT_SIMT)
         assert torch.equal(Kd.diagonal(), torch.ones(64, device=dev)), name
-        assert torch.allclose(Kd, Kd.T, rtol=0, atol=1e-7)
+        assert torch.equal(Kd, Kd.T)
+        # default path (tensor cores for RBF / Matern-3/2, -5/2): GEMM-form distance, diagonal to ~1e-7
+        Kt = kernel_matmat(A, A, I, name, 1.0)
+        assert torch.allclose(Kt, Kd, rtol=0, atol=2e-6), name
         far = kernel_matmat(A, A + 1e4, I, name, 1.0)
         assert torch.isfinite(far).all() and far.abs().max().item() == 0.0
 
