@@ -14,7 +14,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["kmm_api.cu", "kmm_pack.cu", "kmm_simt.cu", "kmm_tc.cu"]
-HEADERS = ["kmm_common.cuh", "kmm_launch.h", "kmm_tc.cuh", os.path.join("..", "..", "include", "rlaopt_b200.h")]
+HEADERS = ["kmm_common.cuh", "kmm_launch.h", "kmm_tmem_ldst.cuh", os.path.join("..", "..", "include", "rlaopt_b200.h")]
 OUT = os.path.join(HERE, "librlaopt_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 

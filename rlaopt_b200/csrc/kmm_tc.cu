@@ -109,27 +109,6 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[tmem] . B[smem]^T
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -152,29 +131,63 @@ __host__ __device__ constexpr uint32_t umma_idesc(int ab_format, int n) {
     return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) | ((uint32_t)(n >> 3) << 17) |
            ((uint32_t)(TC_BM >> 4) << 24);
 }
-constexpr int FMT_F16 = 0, FMT_TF32 = 2;
+constexpr int FMT_F16 = 0;
 
-// round-to-nearest split of an fp32 value into a tf32-representable head and its exact remainder
-__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-    const uint32_t h = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;
-    hi = h;
-    lo = __float_as_uint(v - __uint_as_float(h));
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, one issue slot for two lanes) ----
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
 }
 
-// pointwise kernel function on the squared distance D >= 0 (fast-math forms; rel. error ~2e-7)
+// Pointwise stage, two passes over a thread's 32 entries of one row (DESIGN.md "epilogue"):
+//   pass 1  z_j = phi * D_j (Matern; phi = 1, 3, 5) or -D_j/2 * log2(e) (RBF) from the raw MMA1 sums,
+//           and the row extreme (min D / max exponent argument);
+//   pass 2  P'_j = f(D_j) * 2^E with the power-of-two row scale E folded into the ex2 argument.
+constexpr float TC_LOG2E = 1.44269504088896340736f;
 template <int KID>
-__device__ __forceinline__ float tc_pointwise(float D) {
-    if constexpr (KID == KID_RBF) {
-        return ex2_approx(D * -0.72134752044448170368f);  // exp(-D/2)
-    } else if constexpr (KID == KID_MATERN12) {
-        return ex2_approx(sqrt_approx(D) * -1.44269504088896340736f);
-    } else if constexpr (KID == KID_MATERN32) {
-        const float s = 1.7320508075688772935f * sqrt_approx(D);
-        return (1.0f + s) * ex2_approx(s * -1.44269504088896340736f);
-    } else {  // KID_MATERN52
-        const float s = 2.2360679774997896964f * sqrt_approx(D);
-        return fmaf(D, 1.6666666666666667f, 1.0f + s) * ex2_approx(s * -1.44269504088896340736f);
-    }
+__device__ __forceinline__ float tc_phi() {  // factor folded into the distance before the square root
+    return KID == KID_MATERN32 ? 3.0f : (KID == KID_MATERN52 ? 5.0f : 1.0f);
+}
+// value of the kernel function at z (used once per row for the scale)
+template <int KID>
+__device__ __forceinline__ float tc_value(float z) {
+    const float s = sqrt_approx(fmaxf(z, 0.0f));
+    const float e = ex2_approx(-TC_LOG2E * s);
+    if constexpr (KID == KID_MATERN12) return e;
+    else if constexpr (KID == KID_MATERN32) return (1.0f + s) * e;
+    else return fmaf(s, fmaf(s, 1.0f / 3.0f, 1.0f), 1.0f) * e;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -240,35 +253,60 @@ __global__ void tc_pack_points_kernel(const float* __restrict__ X, int64_t n, in
     norms[i] = (float)(nrm / ((double)s * (double)s));
 }
 
-// V[m][k] -> per (k-chunk, 64-column sub-tile) image of the MMA2 B operand:
-//   [hi | lo] x [K-block of 32 j] x [row c of KP] x 128 B (32 floats, 16 B chunks XOR-swizzled by c & 7)
-__global__ void tc_pack_v_kernel(const float* __restrict__ V, int64_t m, int64_t k, int64_t ldv,
-                                 unsigned char* __restrict__ images, int kp, int64_t sub_tiles, int k_chunks) {
-    const int64_t total = (int64_t)k_chunks * sub_tiles * 2 * kp * 8;  // one thread per 16-byte chunk
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= total) return;
-    const int c = (int)(tid % kp);  // fastest: consecutive threads read consecutive columns of V
-    int64_t rest = tid / kp;
-    const int chunk = (int)(rest % 8);
-    rest /= 8;
-    const int kb = (int)(rest % 2);
-    rest /= 2;
-    const int64_t t = rest % sub_tiles;
-    const int kc = (int)(rest / sub_tiles);
-    const int64_t col = (int64_t)kc * kp + c;
-    alignas(16) uint32_t hi[4];
-    alignas(16) uint32_t lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int64_t j = t * TC_BN + kb * 32 + chunk * 4 + e;
-        const float v = (j < m && col < k) ? V[j * ldv + col] : 0.0f;
-        split_tf32(v, hi[e], lo[e]);
+// V[m][k] -> per (k-chunk, 64-row sub-tile) image of the MMA2 B operand, one block per image:
+//   [hi | lo] x [row c of KP] x 128 B (64 j as fp16, 16 B chunks XOR-swizzled by c & 7) | 16 B trailer {1/s}
+// The tile is scaled by a power of two s (|v s| in [2^14, 2^15)) before the fp16 hi/lo split, so
+// the pair keeps 22 significant bits of every element within 2^-29 of the tile maximum.
+__global__ void __launch_bounds__(256) tc_pack_v_kernel(const float* __restrict__ V, int64_t m, int64_t k, int64_t ldv,
+                                                        unsigned char* __restrict__ images, int kp, int64_t sub_tiles) {
+    extern __shared__ float vt[];  // [64][kp + 1]
+    __shared__ float red[8];
+    const int64_t t = blockIdx.x;
+    const int kc = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int pitch = kp + 1;
+    float mx = 0.0f;
+    for (int e = tid; e < TC_BN * kp; e += 256) {
+        const int j = e / kp, c = e % kp;
+        const int64_t row = t * TC_BN + j, col = (int64_t)kc * kp + c;
+        const float v = (row < m && col < k) ? V[row * ldv + col] : 0.0f;
+        vt[j * pitch + c] = v;
+        const float a = fabsf(v);
+        if (a < 3.0e38f) mx = fmaxf(mx, a);
     }
-    const size_t image_bytes = (size_t)kp * 512;
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    int E = 0;
+    if (mx > 0.0f) E = 14 - ilogbf(mx);
+    E = max(-100, min(100, E));
+    const float s = __uint_as_float((uint32_t)(127 + E) << 23);
+    const size_t image_bytes = (size_t)kp * 256 + 16;
     unsigned char* img = images + ((size_t)kc * sub_tiles + t) * image_bytes;
-    const size_t off = (size_t)kb * kp * 128 + (size_t)c * 128 + (size_t)((chunk ^ (c & 7)) * 16);
-    *reinterpret_cast<uint4*>(img + off) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(img + (size_t)kp * 256 + off) = *reinterpret_cast<const uint4*>(lo);
+    for (int ch = tid; ch < kp * 8; ch += 256) {
+        const int c = ch >> 3, q8 = ch & 7;
+        alignas(16) __half hi[8];
+        alignas(16) __half lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float v = vt[(q8 * 8 + e) * pitch + c] * s;
+            const __half h = __float2half_rn(v);
+            hi[e] = h;
+            lo[e] = __float2half_rn(v - __half2float(h));
+        }
+        const size_t off = (size_t)c * 128 + (size_t)((q8 ^ (c & 7)) * 16);
+        *reinterpret_cast<uint4*>(img + off) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(img + (size_t)kp * 128 + off) = *reinterpret_cast<const uint4*>(lo);
+    }
+    if (tid == 0) {
+        float4 tr;
+        tr.x = __uint_as_float((uint32_t)(127 - E) << 23);  // 1 / s
+        tr.y = tr.z = tr.w = 0.0f;
+        *reinterpret_cast<float4*>(img + (size_t)kp * 256) = tr;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -281,7 +319,9 @@ struct TcParams {
     float* out;
     int64_t ldo, split_stride;
     int64_t n, m;
-    int k, kb, nk1, stages, kid;
+    int k, kb, nk1, kid;
+    int a_stages, v_stages;  // smem ring depths (column-tile images / V images + norms)
+    int nb, la;              // S/P buffers in TMEM, MMA1 look-ahead (tiles)
     float scale_out;
     int64_t sub_tiles;        // ceil(m / 64)
     int tiles_per_split;
@@ -300,60 +340,65 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-// tcgen05.mma with the shared-memory descriptor passed as (lo, hi) words: only the low word
-// (start address) changes between K steps, so advancing an operand is one 32-bit add.
-template <int FMT>
+// tcgen05.mma kind::f16, A from TMEM, B through a shared-memory descriptor passed as (lo, hi)
+// words: only the low word (start address) changes between K steps, so advancing an operand is
+// one 32-bit add.
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi,
                                         uint32_t idesc, uint32_t acc) {
-    if constexpr (FMT == FMT_F16) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            ".reg .b64 bd;\n"
-            "mov.b64 bd, {%2, %3};\n"
-            "setp.ne.b32 p, %5, 0;\n"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n"
-            "}\n" ::"r"(d_tmem),
-            "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            ".reg .b64 bd;\n"
-            "mov.b64 bd, {%2, %3};\n"
-            "setp.ne.b32 p, %5, 0;\n"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n"
-            "}\n" ::"r"(d_tmem),
-            "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
-            : "memory");
-    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 bd;\n"
+        "mov.b64 bd, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
+        : "memory");
 }
 
-// TMEM column map (512 columns x 128 lanes, fp32 words):
-//   [0, 32 KB)              X tile, fp16 hi halves (2 per column)
-//   [32 KB, 64 KB)          X tile, fp16 lo halves
-//   [64 KB, +256)           two S/P buffers: S (64 cols, overwritten in place by P_hi) | P_lo (64 cols)
-//   [64 KB + 256, +2 KP)    two O buffers (one fresh accumulator per sub-tile, alternating)
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
+    if constexpr (N == 32) tmem_ld32(taddr, r);
+    else if constexpr (N == 16) tmem_ld16(taddr, r);
+    else tmem_ld8(taddr, r);
+}
+
+// shared-memory footprint of one V-ring stage: image (hi | lo), 16 B trailer, 64 column norms; 1 KB aligned
+__host__ __device__ constexpr uint32_t tc_v_stage_bytes(int kp) { return (uint32_t)kp * 256 + 1024; }
+
+// TMEM column map (512 columns x 128 lanes, 32-bit words):
+//   [0, 32 KB)                   X tile, fp16 hi halves (two features per column)
+//   [32 KB, 64 KB)               X tile, fp16 lo halves
+//   [64 KB, +64 NB)              NB S/P buffers: S (64 fp32 columns) is overwritten in place by
+//                                P_hi (32 columns of fp16 pairs) | P_lo (32 columns)
+//   [64 KB + 64 NB, +2 KP)       two O buffers (one fresh accumulator per sub-tile, alternating)
 template <int KP>
 __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int KB = p.kb, STAGES = p.stages;
+    const int KB = p.kb, SA = p.a_stages, SV = p.v_stages, NB = p.nb;
     const uint32_t a_img_bytes = (uint32_t)tc_image_bytes(KB);  // hi + lo
-    constexpr uint32_t v_img_bytes = KP * 512;
-    const uint32_t stage_bytes = a_img_bytes + v_img_bytes;
-    float* ny_smem = reinterpret_cast<float*>(smem + (size_t)STAGES * stage_bytes);  // [STAGES][64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ny_smem + STAGES * TC_BN);
-    uint64_t* full = bars;              // [STAGES] producer -> MMA / epilogue
-    uint64_t* empty = full + STAGES;    // [STAGES] MMA -> producer
-    uint64_t* s_full = empty + STAGES;  // [2] MMA1 done
-    uint64_t* p_full = s_full + 2;      // [2] P written (8 warps)
-    uint64_t* p_free = p_full + 2;      // [2] MMA2 done reading P
-    uint64_t* o_full = p_free + 2;      // [2] O buffer complete
-    uint64_t* o_free = o_full + 2;      // [2] O buffer drained (8 warps)
-    uint64_t* a_full = o_free + 2;      // [1] X tile resident in TMEM (8 warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+    constexpr uint32_t v_img_bytes = KP * 256 + 16;             // hi + lo + trailer, as stored in HBM
+    constexpr uint32_t v_stage_bytes = tc_v_stage_bytes(KP);
+    constexpr uint32_t v_norm_off = KP * 256 + 16;
+    unsigned char* a_ring = smem;
+    unsigned char* v_ring = smem + (size_t)SA * a_img_bytes;
+    float* xchg = reinterpret_cast<float*>(v_ring + (size_t)SV * v_stage_bytes);  // [2][2][128] row-max exchange
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 2 * 2 * TC_BM);
+    uint64_t* a_full = bars;             // [SA] producer -> MMA1
+    uint64_t* a_empty = a_full + SA;     // [SA] MMA1 done -> producer
+    uint64_t* v_full = a_empty + SA;     // [SV] producer -> MMA2 / epilogue (norms, V scale)
+    uint64_t* v_empty = v_full + SV;     // [SV] MMA2 done -> producer
+    uint64_t* s_full = v_empty + SV;     // [NB] MMA1 done
+    uint64_t* p_full = s_full + NB;      // [NB] P written (8 warps)
+    uint64_t* p_free = p_full + NB;      // [NB] MMA2 done reading P
+    uint64_t* o_full = p_free + NB;      // [2] O buffer complete
+    uint64_t* o_free = o_full + 2;       // [2] O buffer drained (8 warps)
+    uint64_t* x_full = o_free + 2;       // [1] X tile resident in TMEM (8 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 1);
 
     const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
     const int kc = blockIdx.y;
@@ -362,18 +407,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
     const int T = (int)(t_end - t_begin);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+        for (int s = 0; s < SA; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int s = 0; s < SV; ++s) {
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
+        }
+        for (int b = 0; b < NB; ++b) {
             mbar_init(&s_full[b], 1);
             mbar_init(&p_full[b], TC_EPI_WARPS);
             mbar_init(&p_free[b], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
             mbar_init(&o_full[b], 1);
             mbar_init(&o_free[b], TC_EPI_WARPS);
         }
-        mbar_init(a_full, TC_EPI_WARPS);
+        mbar_init(x_full, TC_EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, 512);
@@ -381,7 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t col_a_hi = 0, col_a_lo = KB * 32, col_sp = KB * 64, col_o = KB * 64 + 256;
+    const uint32_t col_a_hi = 0, col_a_lo = KB * 32, col_sp = KB * 64, col_o = KB * 64 + NB * 64;
 
     const TcHeader* rh = reinterpret_cast<const TcHeader*>(p.rows);
     const TcHeader* ch = reinterpret_cast<const TcHeader*>(p.cols);
@@ -394,40 +445,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             const unsigned char* a_src = col_images + (size_t)t_begin * a_img_bytes;
             const unsigned char* v_src = p.vimg + ((size_t)kc * p.sub_tiles + t_begin) * v_img_bytes;
             const float* n_src = col_norms + t_begin * TC_BN;
-            int s = 0;
-            uint32_t ph = 1;  // a fresh barrier passes a wait on parity 1
+            int sa = 0, sv = 0;
+            uint32_t pha = 1, phv = 1;  // a fresh barrier passes a wait on parity 1
             for (int u = 0; u < T; ++u) {
-                mbar_wait(&empty[s], ph);
-                unsigned char* dst = smem + (size_t)s * stage_bytes;
-                mbar_arrive_expect_tx(&full[s], stage_bytes + TC_BN * 4);
-                bulk_copy_g2s(dst, a_src, a_img_bytes, &full[s]);
-                bulk_copy_g2s(dst + a_img_bytes, v_src, v_img_bytes, &full[s]);
-                bulk_copy_g2s(ny_smem + s * TC_BN, n_src, TC_BN * 4, &full[s]);
+                mbar_wait(&a_empty[sa], pha);
+                mbar_arrive_expect_tx(&a_full[sa], a_img_bytes);
+                bulk_copy_g2s(a_ring + (size_t)sa * a_img_bytes, a_src, a_img_bytes, &a_full[sa]);
+                mbar_wait(&v_empty[sv], phv);
+                unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
+                mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
+                bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
+                bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
                 a_src += a_img_bytes;
                 v_src += v_img_bytes;
                 n_src += TC_BN;
-                if (++s == STAGES) {
-                    s = 0;
-                    ph ^= 1;
+                if (++sa == SA) {
+                    sa = 0;
+                    pha ^= 1;
+                }
+                if (++sv == SV) {
+                    sv = 0;
+                    phv ^= 1;
                 }
             }
         }
     } else if (warp == TC_EPI_WARPS + 1) {
         // =============================== MMA issue ===============================
         // The whole warp runs the (warp-uniform) control flow so addresses live in uniform
-        // registers; one elected lane issues the tcgen05 instructions.
+        // registers; one elected lane issues the tcgen05 instructions.  MMA1 runs LA tiles ahead
+        // of MMA2: with NB >= LA + 2 S/P buffers neither MMA ever waits for the other's completion.
         constexpr uint32_t idesc1 = umma_idesc(FMT_F16, TC_BN);
-        constexpr uint32_t idesc2 = umma_idesc(FMT_TF32, KP);
+        constexpr uint32_t idesc2 = umma_idesc(FMT_F16, KP);
         const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
         const uint32_t desc_lo0 = (uint32_t)(umma_desc_sw128(0) & 0xFFFFFFFFu);
         const int nk1 = p.nk1;
-        const uint32_t smem_base = smem_u32(smem);
+        const uint32_t a_ring_base = smem_u32(a_ring), v_ring_base = smem_u32(v_ring);
         const uint32_t lo_off = (uint32_t)KB * TC_KBLOCK_BYTES;
 
         // S[b] = X . Y_tile^T : hi.lo + lo.hi + hi.hi, one K = 16 step per instruction
         auto issue_mma1 = [&](int b, int s) {
-            const uint32_t d_t = tmem + col_sp + b * 128;
-            const uint32_t img = smem_base + (uint32_t)s * stage_bytes;
+            const uint32_t d_t = tmem + col_sp + b * 64;
+            const uint32_t img = a_ring_base + (uint32_t)s * a_img_bytes;
             const uint32_t dlo_hi = desc_lo0 + (img >> 4);             // Y hi image
             const uint32_t dlo_lo = desc_lo0 + ((img + lo_off) >> 4);  // Y lo image
             if (elect_one()) {
@@ -439,16 +497,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
                     int ks = 0;
 #pragma unroll 1
                     for (; ks + 4 <= nk1; ks += 4) {  // one 64-wide K-block: 4 steps of 32 B inside the 128 B row
-                        umma_ts<FMT_F16>(d_t, a, bd, desc_hi, idesc1, acc);
-                        umma_ts<FMT_F16>(d_t, a + 8, bd + 2, desc_hi, idesc1, 1);
-                        umma_ts<FMT_F16>(d_t, a + 16, bd + 4, desc_hi, idesc1, 1);
-                        umma_ts<FMT_F16>(d_t, a + 24, bd + 6, desc_hi, idesc1, 1);
+                        umma_ts(d_t, a, bd, desc_hi, idesc1, acc);
+                        umma_ts(d_t, a + 8, bd + 2, desc_hi, idesc1, 1);
+                        umma_ts(d_t, a + 16, bd + 4, desc_hi, idesc1, 1);
+                        umma_ts(d_t, a + 24, bd + 6, desc_hi, idesc1, 1);
                         acc = 1;
                         a += 32;
                         bd += TC_KBLOCK_BYTES >> 4;
                     }
                     for (; ks < nk1; ++ks) {
-                        umma_ts<FMT_F16>(d_t, a, bd, desc_hi, idesc1, acc);
+                        umma_ts(d_t, a, bd, desc_hi, idesc1, acc);
                         acc = 1;
                         a += 8;
                         bd += 2;
@@ -457,72 +515,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             }
             __syncwarp();
         };
-        // O[b] = P[b] . V_tile : fresh accumulator per sub-tile, K = 8 (tf32) per instruction
-        auto issue_mma2 = [&](int b, int s) {
-            const uint32_t d_t = tmem + col_o + b * KP;
-            const uint32_t p_hi = tmem + col_sp + b * 128, p_lo = p_hi + 64;
-            const uint32_t img = smem_base + (uint32_t)s * stage_bytes + a_img_bytes;
+        // O[ob] = P[b] . V_tile : fresh accumulator per sub-tile, fp16 pairs, K = 16 per instruction
+        auto issue_mma2 = [&](int b, int ob, int s) {
+            const uint32_t d_t = tmem + col_o + ob * KP;
+            const uint32_t p_hi = tmem + col_sp + b * 64, p_lo = p_hi + 32;
+            const uint32_t img = v_ring_base + (uint32_t)s * v_stage_bytes;
             const uint32_t dlo_hi = desc_lo0 + (img >> 4);
-            const uint32_t dlo_lo = desc_lo0 + ((img + KP * 256) >> 4);
+            const uint32_t dlo_lo = desc_lo0 + ((img + KP * 128) >> 4);
             if (elect_one()) {
 #pragma unroll
                 for (int part = 0; part < 3; ++part) {
                     const uint32_t a = (part == 1 ? p_lo : p_hi);
                     const uint32_t bd = (part == 0 ? dlo_lo : dlo_hi);
 #pragma unroll
-                    for (int ks = 0; ks < TC_BN / 8; ++ks) {
-                        umma_ts<FMT_TF32>(d_t, a + ks * 8, bd + (ks >> 2) * ((KP * 128) >> 4) + (ks & 3) * 2, desc_hi,
-                                          idesc2, (part | ks) != 0);
+                    for (int ks = 0; ks < TC_BN / 16; ++ks) {
+                        umma_ts(d_t, a + ks * 8, bd + ks * 2, desc_hi, idesc2, (part | ks) != 0);
                     }
                 }
             }
             __syncwarp();
         };
-        auto commit = [&](uint64_t* bar) {
-            if (elect_one()) umma_commit(bar);
-            __syncwarp();
-        };
 
-        mbar_wait(a_full, 0);
-        int s1 = 0, s2 = 0;        // ring slots of the tiles MMA1 / MMA2 work on
-        uint32_t ph1 = 0;          // parity of full[s1]
-        if (T > 0) {
-            mbar_wait(&full[0], 0);
+        mbar_wait(x_full, 0);
+        int t1 = 0, b1 = 0, sa = 0;  // next MMA1 tile, its S/P buffer, its A-ring slot
+        uint32_t use1 = 0, pha = 0;   // use count parity of buffer b1, parity of a_full[sa]
+        auto do_mma1 = [&]() {
+            mbar_wait(&a_full[sa], pha);
+            mbar_wait(&p_free[b1], use1 ^ 1);  // MMA2 of tile t1 - NB has consumed P[b1]
             tc_fence_after();
-            issue_mma1(0, 0);
-            commit(&s_full[0]);
-            if (++s1 == STAGES) {
-                s1 = 0;
-                ph1 ^= 1;
-            }
-        }
-        for (int u = 0; u < T; ++u) {
-            const int b = u & 1;
-            const uint32_t par = (uint32_t)((u >> 1) & 1);  // use count parity of buffer b
-            if (u + 1 < T) {
-                const int b1 = b ^ 1;
-                const uint32_t par1 = (uint32_t)(((u + 1) >> 1) & 1);
-                mbar_wait(&full[s1], ph1);
-                mbar_wait(&p_free[b1], par1 ^ 1);  // MMA2 of tile u-1 has consumed P[b1]
-                tc_fence_after();
-                issue_mma1(b1, s1);
-                commit(&s_full[b1]);
-                if (++s1 == STAGES) {
-                    s1 = 0;
-                    ph1 ^= 1;
-                }
-            }
-            mbar_wait(&p_full[b], par);
-            mbar_wait(&o_free[b], par ^ 1);  // O[b] of tile u-2 has been drained
-            tc_fence_after();
-            issue_mma2(b, s2);
+            issue_mma1(b1, sa);
             if (elect_one()) {
-                umma_commit(&empty[s2]);
-                umma_commit(&p_free[b]);
-                umma_commit(&o_full[b]);
+                umma_commit(&s_full[b1]);
+                umma_commit(&a_empty[sa]);
             }
             __syncwarp();
-            if (++s2 == STAGES) s2 = 0;
+            ++t1;
+            if (++b1 == NB) {
+                b1 = 0;
+                use1 ^= 1;
+            }
+            if (++sa == SA) {
+                sa = 0;
+                pha ^= 1;
+            }
+        };
+        for (int i = 0; i < p.la && t1 < T; ++i) do_mma1();
+        int b2 = 0, sv = 0;
+        uint32_t use2 = 0, phv = 0;
+        for (int u = 0; u < T; ++u) {
+            if (t1 < T) do_mma1();
+            const int ob = u & 1;
+            mbar_wait(&p_full[b2], use2);
+            mbar_wait(&v_full[sv], phv);
+            mbar_wait(&o_free[ob], (uint32_t)(((u >> 1) & 1) ^ 1));  // O[ob] of tile u-2 has been drained
+            tc_fence_after();
+            issue_mma2(b2, ob, sv);
+            if (elect_one()) {
+                umma_commit(&v_empty[sv]);
+                umma_commit(&p_free[b2]);
+                umma_commit(&o_full[ob]);
+            }
+            __syncwarp();
+            if (++b2 == NB) {
+                b2 = 0;
+                use2 ^= 1;
+            }
+            if (++sv == SV) {
+                sv = 0;
+                phv ^= 1;
+            }
         }
     } else {
         // =============================== epilogue warps ===============================
@@ -555,84 +616,173 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_full);
+            if (lane == 0) mbar_arrive(x_full);
         }
 
-        float acc[KP / 2];
+        uint64_t acc[KP / 4];  // fp32 pairs
 #pragma unroll
-        for (int c = 0; c < KP / 2; ++c) acc[c] = 0.0f;
+        for (int c = 0; c < KP / 4; ++c) acc[c] = 0ull;
 
-        // fp32 round-to-nearest accumulation of one sub-tile's O buffer into registers
-        auto drain = [&](int b, uint32_t par) {
-            mbar_wait(&o_full[b], par);
+        // acc += O[ob] * dsc: one sub-tile's accumulator, un-scaled and added with round-to-nearest
+        auto drain = [&](int ob, uint32_t par, float dsc) {
+            mbar_wait(&o_full[ob], par);
             tc_fence_after();
+            uint32_t o[KP / 2];
+            tmem_ld_n<KP / 2>(tmem + lane_bits + col_o + ob * KP + h * (KP / 2), o);
+            tmem_wait_ld();
+            const uint64_t d2 = pack2(dsc, dsc);
 #pragma unroll
-            for (int g = 0; g < KP / 16; ++g) {
-                uint32_t o[8];
-                tmem_ld8(tmem + lane_bits + col_o + b * KP + h * (KP / 2) + g * 8, o);
-                tmem_wait_ld();
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[g * 8 + e] += __uint_as_float(o[e]);
-            }
+            for (int e = 0; e < KP / 4; ++e)
+                acc[e] = fma2(pack2(__uint_as_float(o[2 * e]), __uint_as_float(o[2 * e + 1])), d2, acc[e]);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&o_free[b]);
+            if (lane == 0) mbar_arrive(&o_free[ob]);
         };
 
-        int s = 0;
-        uint32_t phs = 0;
+        // per-kernel constants of pass 1: z = S * za + (|y|^2 * zc + zx)
+        float zc;
+        if (p.kid == KID_RBF) zc = -0.5f * TC_LOG2E;
+        else if (p.kid == KID_MATERN32) zc = 3.0f;
+        else if (p.kid == KID_MATERN52) zc = 5.0f;
+        else zc = 1.0f;
+        const uint64_t za2 = pack2(m2c * zc, m2c * zc), zc2 = pack2(zc, zc), zx2 = pack2(nx * zc, nx * zc);
+
+        int b = 0, sv = 0;
+        uint32_t use = 0, phv = 0;
+        float dsc_prev = 0.0f;
         for (int u = 0; u < T; ++u) {
-            const int b = u & 1;
-            const uint32_t par = (uint32_t)((u >> 1) & 1);
-            mbar_wait(&full[s], phs);  // |y|^2 of this sub-tile is in smem
-            mbar_wait(&s_full[b], par);
+            const unsigned char* vst = v_ring + (size_t)sv * v_stage_bytes;
+            mbar_wait(&v_full[sv], phv);  // |y|^2 and the V scale of this sub-tile are in smem
+            mbar_wait(&s_full[b], use);
             tc_fence_after();
-            const uint32_t t_s = tmem + lane_bits + col_sp + b * 128 + h * 32;
-            uint32_t sv[32];
-            tmem_ld32(t_s, sv);
+            const uint32_t t_s = tmem + lane_bits + col_sp + b * 64;
+            uint32_t sv32[32];
+            tmem_ld32(t_s + h * 32, sv32);
             tmem_wait_ld();
-            const float4* nyv = reinterpret_cast<const float4*>(ny_smem + s * TC_BN + h * 32);
-            uint32_t lo[32];
-#define KMM_TC_PW(KID)                                                           \
-    _Pragma("unroll") for (int g = 0; g < 8; ++g) {                              \
-        const float4 ny4 = nyv[g];                                               \
-        const float nyy[4] = {ny4.x, ny4.y, ny4.z, ny4.w};                       \
-        _Pragma("unroll") for (int e = 0; e < 4; ++e) {                          \
-            const int c = g * 4 + e;                                             \
-            float D = fmaf(__uint_as_float(sv[c]), m2c, nx + nyy[e]);            \
-            D = fmaxf(D, 0.0f);                                                  \
-            split_tf32(tc_pointwise<KID>(D), sv[c], lo[c]);                      \
-        }                                                                        \
-    }
-            switch (p.kid) {
-                case KID_RBF: KMM_TC_PW(KID_RBF) break;
-                case KID_MATERN12: KMM_TC_PW(KID_MATERN12) break;
-                case KID_MATERN32: KMM_TC_PW(KID_MATERN32) break;
-                default: KMM_TC_PW(KID_MATERN52) break;
+            const float4* nyv = reinterpret_cast<const float4*>(vst + v_norm_off) + h * 8;
+            const float vinv = *reinterpret_cast<const float*>(vst + KP * 256);
+            // ---- pass 1: z_j and the row extreme ----
+            uint64_t z[16];
+            const bool is_rbf = p.kid == KID_RBF;
+            float ext = is_rbf ? -3.0e38f : 3.0e38f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float4 ny4 = nyv[g];
+                z[2 * g] = fma2(pack2(__uint_as_float(sv32[4 * g]), __uint_as_float(sv32[4 * g + 1])), za2,
+                                fma2(pack2(ny4.x, ny4.y), zc2, zx2));
+                z[2 * g + 1] = fma2(pack2(__uint_as_float(sv32[4 * g + 2]), __uint_as_float(sv32[4 * g + 3])), za2,
+                                    fma2(pack2(ny4.z, ny4.w), zc2, zx2));
             }
-#undef KMM_TC_PW
-            tmem_st32(t_s, sv);        // P_hi in place over S
-            tmem_st32(t_s + 64, lo);   // P_lo
+            if (is_rbf) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float z0, z1;
+                    unpack2(z[i], z0, z1);
+                    ext = max3(ext, z0, z1);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float z0, z1;
+                    unpack2(z[i], z0, z1);
+                    ext = min3(ext, z0, z1);
+                }
+            }
+            // row extreme over the 64 columns: exchange with the warp that owns the other half.
+            // The barrier also orders this warp's tcgen05.st below after the partner's tcgen05.ld
+            // (P_lo of one half lands on the S columns of the other).
+            float* xc = xchg + (u & 1) * (2 * TC_BM);
+            xc[h * TC_BM + row] = ext;
+            tc_fence_before();
+            pair_barrier(1 + q);
+            tc_fence_after();
+            const float other = xc[(h ^ 1) * TC_BM + row];
+            // P' = P * 2^E with max_j P' in [2^14, 2^15): the fp16 hi/lo pair keeps 22 bits of the row's large entries
+            int E;
+            if (is_rbf) {
+                E = 14 - __float2int_rd(fmaxf(fmaxf(ext, other), -200.0f));
+            } else {
+                const float zmin = fminf(ext, other);
+                float pmax;
+                if (p.kid == KID_MATERN12) pmax = tc_value<KID_MATERN12>(zmin);
+                else if (p.kid == KID_MATERN32) pmax = tc_value<KID_MATERN32>(zmin);
+                else pmax = tc_value<KID_MATERN52>(zmin);
+                E = 14 + 127 - (int)((__float_as_uint(pmax) >> 23) & 0xFF);
+            }
+            E = max(0, min(E, 120));
+            const float Ef = (float)E;
+            const float dsc = __uint_as_float((uint32_t)(127 - E) << 23) * vinv;
+            const uint64_t E2 = pack2(Ef, Ef);
+            // ---- pass 2: P'_j, split into fp16 hi / lo pairs ----
+            uint32_t phi[16], plo[16];
+#define KMM_TC_SPLIT(i, P0, P1)                                                   \
+    {                                                                             \
+        const __half2 h2 = __floats2half2_rn(P0, P1);                             \
+        const float2 f2 = __half22float2(h2);                                     \
+        float l0, l1;                                                             \
+        unpack2(sub2(pack2(P0, P1), pack2(f2.x, f2.y)), l0, l1);                  \
+        const __half2 l2 = __floats2half2_rn(l0, l1);                             \
+        phi[i] = *reinterpret_cast<const uint32_t*>(&h2);                         \
+        plo[i] = *reinterpret_cast<const uint32_t*>(&l2);                         \
+    }
+            if (is_rbf) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float a0, a1;
+                    unpack2(add2(z[i], E2), a0, a1);
+                    const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+                    KMM_TC_SPLIT(i, p0, p1)
+                }
+            } else {
+                const uint64_t nl2 = pack2(-TC_LOG2E, -TC_LOG2E), one2 = pack2(1.0f, 1.0f), third2 = pack2(1.0f / 3.0f, 1.0f / 3.0f);
+                const int kid = p.kid;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float z0, z1;
+                    unpack2(z[i], z0, z1);
+                    const float s0 = sqrt_approx(fmaxf(z0, 0.0f)), s1 = sqrt_approx(fmaxf(z1, 0.0f));
+                    const uint64_t s2 = pack2(s0, s1);
+                    float a0, a1;
+                    unpack2(fma2(s2, nl2, E2), a0, a1);
+                    uint64_t pp = pack2(ex2_approx(a0), ex2_approx(a1));
+                    if (kid == KID_MATERN32) pp = mul2(pp, add2(s2, one2));
+                    else if (kid == KID_MATERN52) pp = mul2(pp, fma2(s2, fma2(s2, third2, one2), one2));
+                    float p0, p1;
+                    unpack2(pp, p0, p1);
+                    KMM_TC_SPLIT(i, p0, p1)
+                }
+            }
+#undef KMM_TC_SPLIT
+            tmem_st16(t_s + h * 16, phi);       // P_hi: columns [0, 32) of the buffer
+            tmem_st16(t_s + 32 + h * 16, plo);  // P_lo: columns [32, 64)
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[b]);
             // drain the previous sub-tile's O while the tensor core works on this one
-            if (u > 0) drain(b ^ 1, (uint32_t)(((u - 1) >> 1) & 1));
-            if (++s == STAGES) {
-                s = 0;
-                phs ^= 1;
+            if (u > 0) drain((u - 1) & 1, (uint32_t)(((u - 1) >> 1) & 1), dsc_prev);
+            dsc_prev = dsc;
+            if (++b == NB) {
+                b = 0;
+                use ^= 1;
+            }
+            if (++sv == SV) {
+                sv = 0;
+                phv ^= 1;
             }
         }
-        if (T > 0) drain((T - 1) & 1, (uint32_t)(((T - 1) >> 1) & 1));
+        if (T > 0) drain((T - 1) & 1, (uint32_t)(((T - 1) >> 1) & 1), dsc_prev);
 
         // ---- write this thread's half row of Y ----
         if (grow < p.n) {
             float* dst = p.out + (int64_t)blockIdx.z * p.split_stride + grow * p.ldo;
 #pragma unroll
-            for (int c = 0; c < KP / 2; ++c) {
-                const int col = kc * KP + h * (KP / 2) + c;
-                if (col < p.k) dst[col] = acc[c] * p.scale_out;
+            for (int c = 0; c < KP / 4; ++c) {
+                const int col = kc * KP + h * (KP / 2) + 2 * c;
+                float y0, y1;
+                unpack2(acc[c], y0, y1);
+                if (col < p.k) dst[col] = y0 * p.scale_out;
+                if (col + 1 < p.k) dst[col + 1] = y1 * p.scale_out;
             }
         }
     }
@@ -643,28 +793,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
 }
 
 struct TcPlan {
-    int kb, kp, k_chunks, stages, splits, tiles_per_split;
+    int kb, kp, k_chunks, a_stages, v_stages, nb, la, splits, tiles_per_split;
     int64_t sub_tiles;
     size_t smem_bytes, vimg_bytes, part_bytes;
 };
 
+int tc_env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* pl) {
     if (d < 1 || d > TC_MAX_D || n < 1 || m < 1 || k < 1) return false;
     const int kb = tc_kblocks(d);
-    const int kp_max = kb <= 2 ? 64 : 32;  // TMEM columns: 64*KB (X) + 256 (S/P x2) + 2*KP (O x2) <= 512
     int kp = 16;
-    while (kp < kp_max && kp < k) kp *= 2;
-    const size_t stage = tc_image_bytes(kb) + (size_t)kp * 512;
-    const size_t fixed = 16 * sizeof(uint64_t) + 64;  // barriers + tmem slot (upper bound incl. per-stage barriers below)
-    int stages = 4;
-    while (stages > 1 && stages * (stage + TC_BN * 4 + 2 * sizeof(uint64_t)) + fixed > (size_t)TC_SMEM_LIMIT) --stages;
-    if (stages < 2) return false;
+    while (kp < 64 && kp < k) kp *= 2;
+    // TMEM columns: 64 KB (X hi/lo) + 64 NB (S/P) + 2 KP (O) <= 512
+    int nb = (512 - 64 * kb - 2 * kp) / 64;
+    if (nb > 4) nb = 4;
+    if (nb < 2) return false;
+    nb = max(2, min(nb, tc_env_int("RLAOPT_B200_TC_NB", nb)));
+    int la = nb >= 4 ? 2 : 1;
+    la = max(1, min(nb >= 3 ? nb - 2 : 1, tc_env_int("RLAOPT_B200_TC_LA", la)));
+    // smem: A ring (column-tile images) + V ring (la stages deeper: V of tile t is consumed la tiles after its A)
+    const size_t a_stage = tc_image_bytes(kb), v_stage = tc_v_stage_bytes(kp);
+    const size_t fixed = 2 * 2 * TC_BM * sizeof(float) + 64 * sizeof(uint64_t) + 64;
+    int sa = 4;
+    while (sa > 2 && sa * a_stage + (sa + la) * v_stage + fixed > (size_t)TC_SMEM_LIMIT) --sa;
+    int sv = sa + la;
+    if (sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) return false;
+    if (2 * sa + 2 * sv + 3 * nb + 5 > 64) return false;
     pl->kb = kb;
     pl->kp = kp;
     pl->k_chunks = (int)((k + kp - 1) / kp);
-    pl->stages = stages;
+    pl->a_stages = sa;
+    pl->v_stages = sv;
+    pl->nb = nb;
+    pl->la = la;
     pl->sub_tiles = (m + TC_BN - 1) / TC_BN;
-    pl->smem_bytes = stages * (stage + TC_BN * 4 + 2 * sizeof(uint64_t)) + fixed;
+    pl->smem_bytes = sa * a_stage + sv * v_stage + fixed;
     const int64_t base = ((n + TC_BM - 1) / TC_BM) * pl->k_chunks;
     const int64_t target = (int64_t)sm_count * 2;
     int64_t splits = 1;
@@ -678,7 +845,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     splits = (pl->sub_tiles + tps - 1) / tps;
     pl->splits = (int)splits;
     pl->tiles_per_split = (int)tps;
-    pl->vimg_bytes = (size_t)pl->k_chunks * pl->sub_tiles * kp * 512;
+    pl->vimg_bytes = (size_t)pl->k_chunks * pl->sub_tiles * ((size_t)kp * 256 + 16);
     pl->part_bytes = splits > 1 ? (size_t)splits * n * k * sizeof(float) : 0;
     return true;
 }
@@ -733,9 +900,9 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     unsigned char* vimg = static_cast<unsigned char*>(workspace);
     float* part = reinterpret_cast<float*>(vimg + v_bytes);
     {
-        const int64_t total = (int64_t)pl.k_chunks * pl.sub_tiles * 2 * pl.kp * 8;
-        tc_pack_v_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(V, m, k, ldv, vimg, pl.kp, pl.sub_tiles,
-                                                                              pl.k_chunks);
+        const size_t pack_smem = (size_t)TC_BN * (pl.kp + 1) * sizeof(float);
+        dim3 grid((unsigned)pl.sub_tiles, (unsigned)pl.k_chunks);
+        tc_pack_v_kernel<<<grid, 256, pack_smem, stream>>>(V, m, k, ldv, vimg, pl.kp, pl.sub_tiles);
         cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) return err;
     }
@@ -748,7 +915,10 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     p.k = (int)k;
     p.kb = pl.kb;
     p.nk1 = (int)((d + 15) / 16);
-    p.stages = pl.stages;
+    p.a_stages = pl.a_stages;
+    p.v_stages = pl.v_stages;
+    p.nb = pl.nb;
+    p.la = pl.la;
     p.kid = kid;
     p.sub_tiles = pl.sub_tiles;
     p.tiles_per_split = pl.tiles_per_split;
@@ -767,8 +937,7 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     switch (pl.kp) {
         case 16: err = launch_tc_kp<16>(p, pl, n, stream); break;
         case 32: err = launch_tc_kp<32>(p, pl, n, stream); break;
-        case 64: err = launch_tc_kp<64>(p, pl, n, stream); break;
-        default: err = launch_tc_kp<128>(p, pl, n, stream); break;
+        default: err = launch_tc_kp<64>(p, pl, n, stream); break;
     }
     if (err != cudaSuccess) return err;
     if (pl.splits > 1) return launch_split_reduce<float>(part, pl.splits, n, k, Y, ldy, scale, stream);

@@ -84,8 +84,8 @@ if __name__ == "__main__":
             print(f"positive V period {per}: mean rel {rel.mean().item():.3e} rms {rel.pow(2).mean().sqrt().item():.3e}", flush=True)
     elif which == "perf":
         from rlaopt_b200.kernels import KernelConfig, RBFLinOp, Matern52LinOp
-        for per in ("1",):
-            os.environ["RLAOPT_B200_TC_PERIOD"] = per
+        for per in (("4", "2"), ("3", "1"), ("2", "1")):
+            os.environ["RLAOPT_B200_TC_NB"], os.environ["RLAOPT_B200_TC_LA"] = per
             for cls, n, d, k in ((RBFLinOp, 131072, 128, 64), (Matern52LinOp, 262144, 32, 16)):
                 X = (rnd((n, d), 1) / d**0.5).to(dev)
                 V = rnd((n, k), 2).to(dev)
@@ -100,7 +100,27 @@ if __name__ == "__main__":
                 e1.record()
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 3
-                print(f"period {per} {cls.__name__} n={n} d={d} k={k}: {ms:.2f} ms  {n*n/ms/1e6:.1f} Gentries/s", flush=True)
+                print(f"NB,LA={per} {cls.__name__} n={n} d={d} k={k}: {ms:.2f} ms  {n*n/ms/1e6:.1f} Gentries/s", flush=True)
+    elif which == "range":
+        # tiny kernel values (far-apart clusters): the per-row power-of-two scale keeps relative accuracy
+        for shift in (0.0, 0.5, 1.0, 1.5):
+            n, m, d, k = 512, 4096, 64, 32
+            A1 = rnd((n, d), 1) / d**0.5
+            A2 = rnd((m, d), 2) / d**0.5 + shift
+            V = rnd((m, k), 3)
+            ref = ko.kernel_matmat_gemm_form(A1, A2, V, "rbf", 1.0, dtype=torch.float64)
+            for lay in (TC, _lib.LAYOUT_SIMT):
+                got = ops.kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), "rbf", 1.0, layout=lay)
+                print(f"shift {shift}: layout {lay} rel_err {ko.rel_fro_error(got, ref):.3e} |ref|max {ref.abs().max():.3e}", flush=True)
+        # V with a huge dynamic range across row tiles
+        n, m, d, k = 512, 4096, 64, 32
+        A1 = rnd((n, d), 1) / d**0.5
+        A2 = rnd((m, d), 2) / d**0.5
+        V = rnd((m, k), 3) * torch.logspace(-12, 12, m).unsqueeze(1)
+        ref = ko.kernel_matmat_gemm_form(A1, A2, V, "rbf", 1.0, dtype=torch.float64)
+        for lay in (TC, _lib.LAYOUT_SIMT):
+            got = ops.kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), "rbf", 1.0, layout=lay)
+            print(f"wide V: layout {lay} rel_err {ko.rel_fro_error(got, ref):.3e}", flush=True)
     elif which == "prof":
         from rlaopt_b200.kernels import KernelConfig, RBFLinOp
         n, m, d, k = 148 * 128, 65536, 128, 64
