@@ -298,12 +298,12 @@ def run_ours(args) -> int:
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     ffma_peak = SM_COUNT_B200 * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12
     if layout == _lib.LAYOUT_TC:
-        # fp16 hi/lo split for X.X^T (3 MMAs at the bf16 rate) + TF32 hi/lo split for P.V (3 MMAs at half rate):
-        # tensor work = 6d + 12k bf16-equivalent flop per entry for 2d + 2k algorithmic flop
+        # fp16 hi/lo pairs for both X.X^T and P.V (3 fp16 MMAs each, fp32 accumulate):
+        # tensor work = 6d + 6k fp16 flop per entry for 2d + 2k algorithmic flop
         bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-        peak = bf16 * (2 * d + 2 * k) / (6 * d + 12 * k)
-        bound, peak_note = "tensor", (f"{peaks['_source']} sustained bf16 {bf16:.0f} TFLOP/s x (2d+2k)/(6d+12k) "
-                                      "(split-precision fp32-equivalent)")
+        peak = bf16 * (2 * d + 2 * k) / (6 * d + 6 * k)
+        bound, peak_note = "tensor", (f"{peaks['_source']} sustained bf16 {bf16:.0f} TFLOP/s x (2d+2k)/(6d+6k) "
+                                      "(3-product fp16 split, fp32-equivalent)")
     else:
         peak = ffma_peak
         bound, peak_note = "fp32", f"148 SMs x 128 FFMA lanes x 2 x {sm_max:.0f} MHz ({peaks['_source']} sm_max_mhz)"

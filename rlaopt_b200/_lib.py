@@ -12,7 +12,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librlaopt_b200.so")
+# RLAOPT_B200_LIB selects another build of the same ABI (e.g. the -DKMM_TC_PROFILE diagnostic build)
+LIB_PATH = os.environ.get("RLAOPT_B200_LIB") or os.path.join(_HERE, "csrc", "librlaopt_b200.so")
 
 LAYOUT_SIMT = 0
 LAYOUT_TC = 1

@@ -34,7 +34,7 @@ namespace {
 constexpr int TC_BM = 128;      // rows per CTA (TMEM lanes)
 constexpr int TC_BN = 64;       // K columns per sub-tile
 constexpr int TC_EPI_WARPS = 8; // warps 0..7: pointwise; warp 8: producer; warp 9: MMA issue
-constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 4) * 32;  // warps 8..11: producer, MMA1 issue (even tiles), MMA2 issue, MMA1 issue (odd tiles)
 constexpr int TC_MIN_SPLIT_TILES = 16;  // a column split covers at least 16 sub-tiles (1024 columns)
 constexpr int TC_KBLOCK_BYTES = 64 * 128;  // one K-block of a 64-row image: 64 rows x 128 B
 constexpr int TC_HEADER_BYTES = 256;
@@ -85,6 +85,48 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+// wait on two / three barriers at once: the polls are issued back to back, so the (long) shared-memory
+// round trip of a successful poll is paid once instead of once per barrier
+__device__ __forceinline__ void mbar_wait2(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p, q;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n"
+            "and.pred p, p, q;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(b0)), "r"(p0), "r"(smem_u32(b1)), "r"(p1)
+            : "memory");
+        if (ok) break;
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait3(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1, uint64_t* b2, uint32_t p2) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p, q, r;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 r, [%5], %6;\n"
+            "and.pred p, p, q;\n"
+            "and.pred p, p, r;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(b0)), "r"(p0), "r"(smem_u32(b1)), "r"(p1), "r"(smem_u32(b2)), "r"(p2)
+            : "memory");
+        if (ok) break;
         if (++spins > (1u << 24)) __trap();
     }
 }
@@ -312,6 +354,17 @@ __global__ void __launch_bounds__(256) tc_pack_v_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------
+#ifdef KMM_TC_PROFILE
+__device__ long long g_tc_prof[64];
+#define TC_PROF_DECL long long prof_t = clock64(); long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define TC_PROF(i) { const long long now_ = clock64(); prof_acc[i] += now_ - prof_t; prof_t = now_; }
+#define TC_PROF_FLUSH(base) if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) { for (int i_ = 0; i_ < 8; ++i_) g_tc_prof[(base) + i_] = prof_acc[i_]; }
+#else
+#define TC_PROF_DECL
+#define TC_PROF(i) {}
+#define TC_PROF_FLUSH(base) {}
+#endif
+
 struct TcParams {
     const unsigned char* rows;  // packed row operand
     const unsigned char* cols;  // packed column operand
@@ -322,6 +375,7 @@ struct TcParams {
     int k, kb, nk1, kid;
     int a_stages, v_stages;  // smem ring depths (column-tile images / V images + norms)
     int nb, la;              // S/P buffers in TMEM, MMA1 look-ahead (tiles)
+    int diag;                // RLAOPT_B200_TC_DIAG knock-outs (profiling only): 1 no MMA, 2 no pointwise, 4 no drain, 8 no loads
     float scale_out;
     int64_t sub_tiles;        // ceil(m / 64)
     int tiles_per_split;
@@ -356,8 +410,6 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32
         "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
         : "memory");
 }
-
-__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 template <int N>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
@@ -417,12 +469,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         }
         for (int b = 0; b < NB; ++b) {
             mbar_init(&s_full[b], 1);
-            mbar_init(&p_full[b], TC_EPI_WARPS);
+            mbar_init(&p_full[b], TC_EPI_WARPS / 2);
             mbar_init(&p_free[b], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&o_full[b], 1);
-            mbar_init(&o_free[b], TC_EPI_WARPS);
+            mbar_init(&o_free[b], TC_EPI_WARPS / 2);
         }
         mbar_init(x_full, TC_EPI_WARPS);
         fence_barrier_init();
@@ -439,6 +491,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
     const float* col_norms = reinterpret_cast<const float*>(p.cols + tc_norm_offset());
     const unsigned char* col_images = p.cols + tc_image_offset(p.m);
 
+    if (warp >= TC_EPI_WARPS) {
+    // registers move from this warpgroup (producer, MMA issue, two idle warps) to the epilogue warpgroups
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == TC_EPI_WARPS) {
         // =============================== producer ===============================
         if (lane == 0) {
@@ -449,6 +504,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             uint32_t pha = 1, phv = 1;  // a fresh barrier passes a wait on parity 1
             for (int u = 0; u < T; ++u) {
                 mbar_wait(&a_empty[sa], pha);
+                if (p.diag & 8) {
+                    mbar_arrive(&a_full[sa]);
+                    mbar_wait(&v_empty[sv], phv);
+                    mbar_arrive(&v_full[sv]);
+                } else {
                 mbar_arrive_expect_tx(&a_full[sa], a_img_bytes);
                 bulk_copy_g2s(a_ring + (size_t)sa * a_img_bytes, a_src, a_img_bytes, &a_full[sa]);
                 mbar_wait(&v_empty[sv], phv);
@@ -456,6 +516,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
                 mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
                 bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
                 bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
+                }
                 a_src += a_img_bytes;
                 v_src += v_img_bytes;
                 n_src += TC_BN;
@@ -469,8 +530,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
                 }
             }
         }
-    } else if (warp == TC_EPI_WARPS + 1) {
-        // =============================== MMA issue ===============================
+    } else {
+        // =============================== MMA issue (warps 9, 11: MMA1, warp 10: MMA2) ===============================
         // The whole warp runs the (warp-uniform) control flow so addresses live in uniform
         // registers; one elected lane issues the tcgen05 instructions.  MMA1 runs LA tiles ahead
         // of MMA2: with NB >= LA + 2 S/P buffers neither MMA ever waits for the other's completion.
@@ -488,7 +549,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             const uint32_t img = a_ring_base + (uint32_t)s * a_img_bytes;
             const uint32_t dlo_hi = desc_lo0 + (img >> 4);             // Y hi image
             const uint32_t dlo_lo = desc_lo0 + ((img + lo_off) >> 4);  // Y lo image
-            if (elect_one()) {
+            if (!(p.diag & 1) && elect_one()) {
                 uint32_t acc = 0;
 #pragma unroll 1
                 for (int part = 0; part < 3; ++part) {
@@ -522,7 +583,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             const uint32_t img = v_ring_base + (uint32_t)s * v_stage_bytes;
             const uint32_t dlo_hi = desc_lo0 + (img >> 4);
             const uint32_t dlo_lo = desc_lo0 + ((img + KP * 128) >> 4);
-            if (elect_one()) {
+            if (!(p.diag & 1) && elect_one()) {
 #pragma unroll
                 for (int part = 0; part < 3; ++part) {
                     const uint32_t a = (part == 1 ? p_lo : p_hi);
@@ -536,56 +597,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             __syncwarp();
         };
 
-        mbar_wait(x_full, 0);
-        int t1 = 0, b1 = 0, sa = 0;  // next MMA1 tile, its S/P buffer, its A-ring slot
-        uint32_t use1 = 0, pha = 0;   // use count parity of buffer b1, parity of a_full[sa]
-        auto do_mma1 = [&]() {
-            mbar_wait(&a_full[sa], pha);
-            mbar_wait(&p_free[b1], use1 ^ 1);  // MMA2 of tile t1 - NB has consumed P[b1]
-            tc_fence_after();
-            issue_mma1(b1, sa);
-            if (elect_one()) {
-                umma_commit(&s_full[b1]);
-                umma_commit(&a_empty[sa]);
+        if (warp != TC_EPI_WARPS + 2) {
+            // ---- MMA1 issuers: warp 9 takes the even sub-tiles, warp 11 the odd ones, each running ahead of
+            // MMA2 as far as the NB S/P buffers and the A ring allow; while one of them polls its barriers the
+            // other's instructions keep the tensor pipe fed ----
+            const int par = (warp == TC_EPI_WARPS + 1) ? 0 : 1;
+            mbar_wait(x_full, 0);
+            int b1 = par % NB, sa = par % SA;
+            uint32_t use1 = (uint32_t)((par / NB) & 1), pha = (uint32_t)((par / SA) & 1);
+            TC_PROF_DECL
+            for (int t1 = par; t1 < T; t1 += 2) {
+                TC_PROF(7)
+                // A image landed; MMA2 of tile t1 - NB has consumed P[b1]
+                mbar_wait2(&a_full[sa], pha, &p_free[b1], use1 ^ 1);
+                TC_PROF(0)
+                tc_fence_after();
+                issue_mma1(b1, sa);
+                if (elect_one()) {
+                    umma_commit(&s_full[b1]);
+                    umma_commit(&a_empty[sa]);
+                }
+                __syncwarp();
+                TC_PROF(2)
+                b1 += 2;
+                if (b1 >= NB) {
+                    b1 -= NB;
+                    use1 ^= 1;
+                }
+                sa += 2;
+                if (sa >= SA) {
+                    sa -= SA;
+                    pha ^= 1;
+                }
             }
-            __syncwarp();
-            ++t1;
-            if (++b1 == NB) {
-                b1 = 0;
-                use1 ^= 1;
+            if (par == 0) TC_PROF_FLUSH(0)
+        } else {
+            // ---- MMA2 issuer ----
+            int b2 = 0, sv = 0;
+            uint32_t use2 = 0, phv = 0;
+            TC_PROF_DECL
+            for (int u = 0; u < T; ++u) {
+                const int ob = u & 1;
+                TC_PROF(7)
+                // P written; V image landed; O[ob] of tile u - 2 has been drained
+                mbar_wait3(&p_full[b2], use2, &v_full[sv], phv, &o_free[ob], (uint32_t)(((u >> 1) & 1) ^ 1));
+                TC_PROF(3)
+                tc_fence_after();
+                issue_mma2(b2, ob, sv);
+                if (elect_one()) {
+                    umma_commit(&v_empty[sv]);
+                    umma_commit(&p_free[b2]);
+                    umma_commit(&o_full[ob]);
+                }
+                __syncwarp();
+                TC_PROF(6)
+                if (++b2 == NB) {
+                    b2 = 0;
+                    use2 ^= 1;
+                }
+                if (++sv == SV) {
+                    sv = 0;
+                    phv ^= 1;
+                }
             }
-            if (++sa == SA) {
-                sa = 0;
-                pha ^= 1;
-            }
-        };
-        for (int i = 0; i < p.la && t1 < T; ++i) do_mma1();
-        int b2 = 0, sv = 0;
-        uint32_t use2 = 0, phv = 0;
-        for (int u = 0; u < T; ++u) {
-            if (t1 < T) do_mma1();
-            const int ob = u & 1;
-            mbar_wait(&p_full[b2], use2);
-            mbar_wait(&v_full[sv], phv);
-            mbar_wait(&o_free[ob], (uint32_t)(((u >> 1) & 1) ^ 1));  // O[ob] of tile u-2 has been drained
-            tc_fence_after();
-            issue_mma2(b2, ob, sv);
-            if (elect_one()) {
-                umma_commit(&v_empty[sv]);
-                umma_commit(&p_free[b2]);
-                umma_commit(&o_full[ob]);
-            }
-            __syncwarp();
-            if (++b2 == NB) {
-                b2 = 0;
-                use2 ^= 1;
-            }
-            if (++sv == SV) {
-                sv = 0;
-                phv ^= 1;
-            }
+            TC_PROF_FLUSH(24)
         }
+    }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // =============================== epilogue warps ===============================
         const int q = warp & 3;   // TMEM lane quarter this warp may access
         const int h = warp >> 2;  // column half of the sub-tile / of O handled by this warp
@@ -619,24 +698,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             if (lane == 0) mbar_arrive(x_full);
         }
 
-        uint64_t acc[KP / 4];  // fp32 pairs
+        // Two warpgroups ping-pong over the sub-tiles (warpgroup g owns tiles u = g, g+2, ...): each
+        // thread owns one full row of S (64 entries), so the row scale needs no exchange and the two
+        // warps that share an SM sub-partition work on different tiles, covering each other's
+        // TMEM / MUFU latencies.
+        const int g = h;
+        uint64_t acc[KP / 2];  // fp32 pairs: this warpgroup's partial row of Y (KP columns)
 #pragma unroll
-        for (int c = 0; c < KP / 4; ++c) acc[c] = 0ull;
+        for (int c = 0; c < KP / 2; ++c) acc[c] = 0ull;
 
-        // acc += O[ob] * dsc: one sub-tile's accumulator, un-scaled and added with round-to-nearest
-        auto drain = [&](int ob, uint32_t par, float dsc) {
-            mbar_wait(&o_full[ob], par);
+        // acc += O[g] * dsc: one sub-tile's accumulator, un-scaled and added with round-to-nearest
+        auto drain = [&](uint32_t par, float dsc) {
+            mbar_wait(&o_full[g], par);
             tc_fence_after();
-            uint32_t o[KP / 2];
-            tmem_ld_n<KP / 2>(tmem + lane_bits + col_o + ob * KP + h * (KP / 2), o);
-            tmem_wait_ld();
             const uint64_t d2 = pack2(dsc, dsc);
 #pragma unroll
-            for (int e = 0; e < KP / 4; ++e)
-                acc[e] = fma2(pack2(__uint_as_float(o[2 * e]), __uint_as_float(o[2 * e + 1])), d2, acc[e]);
+            for (int c0 = 0; c0 < KP; c0 += 32) {
+                constexpr int W = KP < 32 ? KP : 32;
+                uint32_t o[W];
+                tmem_ld_n<W>(tmem + lane_bits + col_o + g * KP + c0, o);
+                tmem_wait_ld();
+                if (!(p.diag & 4))
+#pragma unroll
+                for (int e = 0; e < W / 2; ++e)
+                    acc[c0 / 2 + e] = fma2(pack2(__uint_as_float(o[2 * e]), __uint_as_float(o[2 * e + 1])), d2, acc[c0 / 2 + e]);
+            }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&o_free[ob]);
+            if (lane == 0) mbar_arrive(&o_free[g]);
         };
 
         // per-kernel constants of pass 1: z = S * za + (|y|^2 * zc + zx)
@@ -646,75 +735,94 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         else if (p.kid == KID_MATERN52) zc = 5.0f;
         else zc = 1.0f;
         const uint64_t za2 = pack2(m2c * zc, m2c * zc), zc2 = pack2(zc, zc), zx2 = pack2(nx * zc, nx * zc);
+        const bool is_rbf = p.kid == KID_RBF;
+        const int kid = p.kid;
 
-        int b = 0, sv = 0;
-        uint32_t use = 0, phv = 0;
+        int b = g % NB, sv = g % SV;
+        uint32_t use = (uint32_t)((g / NB) & 1), phv = (uint32_t)((g / SV) & 1);
         float dsc_prev = 0.0f;
-        for (int u = 0; u < T; ++u) {
+        TC_PROF_DECL
+        for (int u = g; u < T; u += 2) {
             const unsigned char* vst = v_ring + (size_t)sv * v_stage_bytes;
-            mbar_wait(&v_full[sv], phv);  // |y|^2 and the V scale of this sub-tile are in smem
-            mbar_wait(&s_full[b], use);
+            TC_PROF(7)
+            // |y|^2 and the V scale of this sub-tile are in smem; MMA1 has written S[b]
+            mbar_wait2(&v_full[sv], phv, &s_full[b], use);
+            TC_PROF(1)
             tc_fence_after();
             const uint32_t t_s = tmem + lane_bits + col_sp + b * 64;
-            uint32_t sv32[32];
-            tmem_ld32(t_s + h * 32, sv32);
+            uint32_t s0[32], s1[32];
+            tmem_ld32(t_s, s0);
+            tmem_ld32(t_s + 32, s1);
             tmem_wait_ld();
-            const float4* nyv = reinterpret_cast<const float4*>(vst + v_norm_off) + h * 8;
+            TC_PROF(2)
+            const float4* nyv = reinterpret_cast<const float4*>(vst + v_norm_off);
             const float vinv = *reinterpret_cast<const float*>(vst + KP * 256);
-            // ---- pass 1: z_j and the row extreme ----
-            uint64_t z[16];
-            const bool is_rbf = p.kid == KID_RBF;
-            float ext = is_rbf ? -3.0e38f : 3.0e38f;
+            if (p.diag & 2) {
+                uint32_t phi[16], plo[16];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const float4 ny4 = nyv[g];
-                z[2 * g] = fma2(pack2(__uint_as_float(sv32[4 * g]), __uint_as_float(sv32[4 * g + 1])), za2,
+                for (int i = 0; i < 16; ++i) phi[i] = s0[i] + s1[i], plo[i] = s0[16 + i] + s1[16 + i];
+                tmem_st16(t_s, phi);
+                tmem_st16(t_s + 16, plo);
+                tmem_st16(t_s + 32, plo);
+                tmem_st16(t_s + 48, phi);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[b]);
+                TC_PROF(4)
+                if (u >= 2) drain((uint32_t)(((u - 2) >> 1) & 1), 1.0f);
+                TC_PROF(5)
+            } else {
+            // ---- pass 1: z_j and the row extreme ----
+            uint64_t z[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 ny4 = nyv[i];
+                z[2 * i] = fma2(pack2(__uint_as_float(s0[4 * i]), __uint_as_float(s0[4 * i + 1])), za2,
                                 fma2(pack2(ny4.x, ny4.y), zc2, zx2));
-                z[2 * g + 1] = fma2(pack2(__uint_as_float(sv32[4 * g + 2]), __uint_as_float(sv32[4 * g + 3])), za2,
+                z[2 * i + 1] = fma2(pack2(__uint_as_float(s0[4 * i + 2]), __uint_as_float(s0[4 * i + 3])), za2,
                                     fma2(pack2(ny4.z, ny4.w), zc2, zx2));
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 ny4 = nyv[8 + i];
+                z[16 + 2 * i] = fma2(pack2(__uint_as_float(s1[4 * i]), __uint_as_float(s1[4 * i + 1])), za2,
+                                     fma2(pack2(ny4.x, ny4.y), zc2, zx2));
+                z[16 + 2 * i + 1] = fma2(pack2(__uint_as_float(s1[4 * i + 2]), __uint_as_float(s1[4 * i + 3])), za2,
+                                         fma2(pack2(ny4.z, ny4.w), zc2, zx2));
+            }
+            float ext = is_rbf ? -3.0e38f : 3.0e38f;
             if (is_rbf) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 32; ++i) {
                     float z0, z1;
                     unpack2(z[i], z0, z1);
                     ext = max3(ext, z0, z1);
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 32; ++i) {
                     float z0, z1;
                     unpack2(z[i], z0, z1);
                     ext = min3(ext, z0, z1);
                 }
             }
-            // row extreme over the 64 columns: exchange with the warp that owns the other half.
-            // The barrier also orders this warp's tcgen05.st below after the partner's tcgen05.ld
-            // (P_lo of one half lands on the S columns of the other).
-            float* xc = xchg + (u & 1) * (2 * TC_BM);
-            xc[h * TC_BM + row] = ext;
-            tc_fence_before();
-            pair_barrier(1 + q);
-            tc_fence_after();
-            const float other = xc[(h ^ 1) * TC_BM + row];
             // P' = P * 2^E with max_j P' in [2^14, 2^15): the fp16 hi/lo pair keeps 22 bits of the row's large entries
             int E;
             if (is_rbf) {
-                E = 14 - __float2int_rd(fmaxf(fmaxf(ext, other), -200.0f));
+                E = 14 - __float2int_rd(fmaxf(ext, -200.0f));
             } else {
-                const float zmin = fminf(ext, other);
                 float pmax;
-                if (p.kid == KID_MATERN12) pmax = tc_value<KID_MATERN12>(zmin);
-                else if (p.kid == KID_MATERN32) pmax = tc_value<KID_MATERN32>(zmin);
-                else pmax = tc_value<KID_MATERN52>(zmin);
+                if (kid == KID_MATERN12) pmax = tc_value<KID_MATERN12>(ext);
+                else if (kid == KID_MATERN32) pmax = tc_value<KID_MATERN32>(ext);
+                else pmax = tc_value<KID_MATERN52>(ext);
                 E = 14 + 127 - (int)((__float_as_uint(pmax) >> 23) & 0xFF);
             }
             E = max(0, min(E, 120));
             const float Ef = (float)E;
             const float dsc = __uint_as_float((uint32_t)(127 - E) << 23) * vinv;
             const uint64_t E2 = pack2(Ef, Ef);
-            // ---- pass 2: P'_j, split into fp16 hi / lo pairs ----
-            uint32_t phi[16], plo[16];
+            // ---- pass 2: P'_j, split into fp16 hi / lo pairs, 32 entries per TMEM store ----
 #define KMM_TC_SPLIT(i, P0, P1)                                                   \
     {                                                                             \
         const __half2 h2 = __floats2half2_rn(P0, P1);                             \
@@ -725,64 +833,91 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         phi[i] = *reinterpret_cast<const uint32_t*>(&h2);                         \
         plo[i] = *reinterpret_cast<const uint32_t*>(&l2);                         \
     }
-            if (is_rbf) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float a0, a1;
-                    unpack2(add2(z[i], E2), a0, a1);
-                    const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
-                    KMM_TC_SPLIT(i, p0, p1)
-                }
-            } else {
-                const uint64_t nl2 = pack2(-TC_LOG2E, -TC_LOG2E), one2 = pack2(1.0f, 1.0f), third2 = pack2(1.0f / 3.0f, 1.0f / 3.0f);
-                const int kid = p.kid;
+            for (int half = 0; half < 2; ++half) {
+                uint32_t phi[16], plo[16];
+                if (is_rbf) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float z0, z1;
-                    unpack2(z[i], z0, z1);
-                    const float s0 = sqrt_approx(fmaxf(z0, 0.0f)), s1 = sqrt_approx(fmaxf(z1, 0.0f));
-                    const uint64_t s2 = pack2(s0, s1);
-                    float a0, a1;
-                    unpack2(fma2(s2, nl2, E2), a0, a1);
-                    uint64_t pp = pack2(ex2_approx(a0), ex2_approx(a1));
-                    if (kid == KID_MATERN32) pp = mul2(pp, add2(s2, one2));
-                    else if (kid == KID_MATERN52) pp = mul2(pp, fma2(s2, fma2(s2, third2, one2), one2));
-                    float p0, p1;
-                    unpack2(pp, p0, p1);
-                    KMM_TC_SPLIT(i, p0, p1)
+                    for (int i = 0; i < 16; ++i) {
+                        float a0, a1;
+                        unpack2(add2(z[half * 16 + i], E2), a0, a1);
+                        const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+                        KMM_TC_SPLIT(i, p0, p1)
+                    }
+                } else {
+                    const uint64_t nl2 = pack2(-TC_LOG2E, -TC_LOG2E), one2 = pack2(1.0f, 1.0f),
+                                   third2 = pack2(1.0f / 3.0f, 1.0f / 3.0f);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float z0, z1;
+                        unpack2(z[half * 16 + i], z0, z1);
+                        const float r0 = sqrt_approx(fmaxf(z0, 0.0f)), r1 = sqrt_approx(fmaxf(z1, 0.0f));
+                        const uint64_t r2 = pack2(r0, r1);
+                        float a0, a1;
+                        unpack2(fma2(r2, nl2, E2), a0, a1);
+                        uint64_t pp = pack2(ex2_approx(a0), ex2_approx(a1));
+                        if (kid == KID_MATERN32) pp = mul2(pp, add2(r2, one2));
+                        else if (kid == KID_MATERN52) pp = mul2(pp, fma2(r2, fma2(r2, third2, one2), one2));
+                        float p0, p1;
+                        unpack2(pp, p0, p1);
+                        KMM_TC_SPLIT(i, p0, p1)
+                    }
                 }
+                tmem_st16(t_s + half * 16, phi);       // P_hi: columns [0, 32) of the buffer
+                tmem_st16(t_s + 32 + half * 16, plo);  // P_lo: columns [32, 64)
             }
 #undef KMM_TC_SPLIT
-            tmem_st16(t_s + h * 16, phi);       // P_hi: columns [0, 32) of the buffer
-            tmem_st16(t_s + 32 + h * 16, plo);  // P_lo: columns [32, 64)
+            TC_PROF(3)
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[b]);
-            // drain the previous sub-tile's O while the tensor core works on this one
-            if (u > 0) drain((u - 1) & 1, (uint32_t)(((u - 1) >> 1) & 1), dsc_prev);
+            TC_PROF(4)
+            // drain this warpgroup's previous sub-tile while the tensor core works on this one
+            if (u >= 2) drain((uint32_t)(((u - 2) >> 1) & 1), dsc_prev);
+            TC_PROF(5)
             dsc_prev = dsc;
-            if (++b == NB) {
-                b = 0;
+            }
+            b += 2;
+            if (b >= NB) {
+                b -= NB;
                 use ^= 1;
             }
-            if (++sv == SV) {
-                sv = 0;
+            sv += 2;
+            if (sv >= SV) {
+                sv -= SV;
                 phv ^= 1;
             }
         }
-        if (T > 0) drain((T - 1) & 1, (uint32_t)(((T - 1) >> 1) & 1), dsc_prev);
+        if (warp == 0) TC_PROF_FLUSH(8)
+        else if (warp == 4) TC_PROF_FLUSH(16)
+        {
+            const int last = ((T - 1 - g) >> 1) * 2 + g;  // this warpgroup's last tile (T > g)
+            if (T > g) drain((uint32_t)((last >> 1) & 1), (p.diag & 2) ? 1.0f : dsc_prev);
+        }
 
-        // ---- write this thread's half row of Y ----
-        if (grow < p.n) {
-            float* dst = p.out + (int64_t)blockIdx.z * p.split_stride + grow * p.ldo;
+        // ---- Y rows = warpgroup 0 partial + warpgroup 1 partial (through smem; all MMAs and loads are done) ----
+        float* ysm = reinterpret_cast<float*>(smem);  // [128][KP + 1], reuses the A ring
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // both warpgroups have drained their last tile
+        if (g == 1) {
 #pragma unroll
-            for (int c = 0; c < KP / 4; ++c) {
-                const int col = kc * KP + h * (KP / 2) + 2 * c;
+            for (int c = 0; c < KP / 2; ++c) {
                 float y0, y1;
                 unpack2(acc[c], y0, y1);
-                if (col < p.k) dst[col] = y0 * p.scale_out;
-                if (col + 1 < p.k) dst[col + 1] = y1 * p.scale_out;
+                ysm[row * (KP + 1) + 2 * c] = y0;
+                ysm[row * (KP + 1) + 2 * c + 1] = y1;
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (g == 0 && grow < p.n) {
+            float* dst = p.out + (int64_t)blockIdx.z * p.split_stride + grow * p.ldo;
+#pragma unroll
+            for (int c = 0; c < KP / 2; ++c) {
+                const int col = kc * KP + 2 * c;
+                float y0, y1;
+                unpack2(acc[c], y0, y1);
+                if (col < p.k) dst[col] = (y0 + ysm[row * (KP + 1) + 2 * c]) * p.scale_out;
+                if (col + 1 < p.k) dst[col + 1] = (y1 + ysm[row * (KP + 1) + 2 * c + 1]) * p.scale_out;
             }
         }
     }
@@ -852,6 +987,12 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
 
 }  // namespace
 
+#ifdef KMM_TC_PROFILE
+extern "C" int kmm_tc_prof_read(long long* host64) {
+    return (int)cudaMemcpyFromSymbol(host64, g_tc_prof, sizeof(long long) * 64);
+}
+#endif
+
 bool tc_supported_d(int64_t d) { return d >= 1 && d <= TC_MAX_D; }
 bool tc_supported_k(int64_t k) { return k >= 1; }
 
@@ -919,6 +1060,7 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     p.v_stages = pl.v_stages;
     p.nb = pl.nb;
     p.la = pl.la;
+    p.diag = tc_env_int("RLAOPT_B200_TC_DIAG", 0);
     p.kid = kid;
     p.sub_tiles = pl.sub_tiles;
     p.tiles_per_split = pl.tiles_per_split;

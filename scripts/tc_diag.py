@@ -101,6 +101,48 @@ if __name__ == "__main__":
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 3
                 print(f"NB,LA={per} {cls.__name__} n={n} d={d} k={k}: {ms:.2f} ms  {n*n/ms/1e6:.1f} Gentries/s", flush=True)
+    elif which == "knock":
+        from rlaopt_b200.kernels import KernelConfig, RBFLinOp, Matern52LinOp
+        for diag in ("0", "1", "2", "4", "6", "8", "9", "3", "15"):
+            os.environ["RLAOPT_B200_TC_DIAG"] = diag
+            for cls, n, d, k in ((RBFLinOp, 131072, 128, 64), (Matern52LinOp, 262144, 32, 16)):
+                X = (rnd((n, d), 1) / d**0.5).to(dev)
+                V = rnd((n, k), 2).to(dev)
+                op = cls(X, X, KernelConfig(lengthscale=1.0))
+                for _ in range(2):
+                    Y = op @ V
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    Y = op @ V
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 3
+                print(f"diag {diag} {cls.__name__} n={n} d={d} k={k}: {ms:.2f} ms  {n*n/ms/1e6:.1f} Gentries/s", flush=True)
+    elif which == "prof2":
+        # per-section cycle counters of CTA 0 (needs the -DKMM_TC_PROFILE build, RLAOPT_B200_LIB=...)
+        import ctypes
+        from rlaopt_b200.kernels import KernelConfig, RBFLinOp
+        lib = _lib.load()
+        n, d, k = 131072, 128, 64
+        X = (rnd((n, d), 1) / d**0.5).to(dev)
+        V = rnd((n, k), 2).to(dev)
+        op = RBFLinOp(X, X, KernelConfig(lengthscale=1.0))
+        for diag in ("0", "2", "1", "3"):
+            os.environ["RLAOPT_B200_TC_DIAG"] = diag
+            for _ in range(2):
+                Y = op @ V
+            torch.cuda.synchronize()
+            buf = (ctypes.c_longlong * 64)()
+            lib.kmm_tc_prof_read(buf)
+            tiles = n // 64
+            names_m = ["w_a_full", "w_p_free", "issue1+commit", "w_p_full", "w_v_full", "w_o_free", "issue2+commit", "other"]
+            names_e = ["w_v_full", "w_s_full", "ld S", "compute+st", "wait st+arrive", "drain", "-", "other"]
+            print(f"diag {diag}: MMA1 warp clk/tile:", {nm: round(buf[i] / tiles, 1) for i, nm in enumerate(names_m)}, "total", round(sum(buf[0:8]) / tiles, 1), flush=True)
+            print(f"   MMA2 warp clk/tile:", {nm: round(buf[24 + i] / tiles, 1) for i, nm in enumerate(names_m)}, "total", round(sum(buf[24:32]) / tiles, 1), flush=True)
+            for base, nm in ((8, "epi warp0"), (16, "epi warp4")):
+                print(f"   {nm} clk per own tile:", {x: round(buf[base + i] / (tiles / 2), 1) for i, x in enumerate(names_e)}, "total", round(sum(buf[base:base + 8]) / (tiles / 2), 1), flush=True)
     elif which == "range":
         # tiny kernel values (far-apart clusters): the per-row power-of-two scale keeps relative accuracy
         for shift in (0.0, 0.5, 1.0, 1.5):
