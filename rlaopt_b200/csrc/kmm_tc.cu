@@ -2,24 +2,24 @@
 //
 //   Y[i,:] = c * sum_j f(|x_i|^2 + |y_j|^2 - 2 x_i.y_j) V[j,:]
 //
-// flash-attention-shaped, one CTA per 128 output rows, streaming 64-column sub-tiles:
+// flash-attention-shaped, one CTA per 128 output rows, streaming 64-column sub-tiles.
+// 12 warps:
 //
-//   producer warp   cp.async.bulk (TMA engine, UBLKCP) of pre-swizzled tile images
-//                   {Y-tile fp16 hi/lo, V-tile tf32 hi/lo, |y|^2} into a smem ring
-//   MMA warp        MMA1  S  = X.Y^T     kind::f16, A = X tile resident in TMEM,
-//                                        3 products hi.lo + lo.hi + hi.hi, fp32 accumulate
-//                   MMA2  O += P.V       kind::tf32, A = P from TMEM (in place over S),
-//                                        3 products hi.lo + lo.hi + hi.hi
-//   8 epilogue warps  tcgen05.ld S -> D = |x|^2+|y|^2-2S -> P = f(D) in registers
-//                   -> split P into tf32 hi/lo -> tcgen05.st back into TMEM;
-//                   -> drain the previous sub-tile's O from TMEM into fp32 registers: each
-//                   sub-tile gets a fresh TMEM accumulator and the long column sum is done
-//                   with round-to-nearest FADDs (the tensor core accumulates with
-//                   truncation, measured bias -1e-5 over 1024 columns)
+//   warp 8 (producer)   cp.async.bulk (TMA engine, UBLKCP) of pre-swizzled tile images into two smem
+//                       rings: A ring {Y-tile fp16 hi|lo}, V ring {V-tile fp16 hi|lo, 1/s_V, |y|^2}
+//   warps 9, 11 (MMA1)  S[b] = X.Y^T   kind::f16, A = X tile resident in TMEM, 3 products
+//                       hi.lo + lo.hi + hi.hi, fp32 accumulate; even / odd sub-tiles
+//   warp 10 (MMA2)      O[u&1] = P'[b].V'   kind::f16, A = P' from TMEM (in place over S), 3 products
+//   warps 0-3 / 4-7     two epilogue warpgroups ping-pong over the sub-tiles; a thread owns one full row:
+//                       tcgen05.ld S -> z = c1*S + c2*|y|^2 + c3 (packed FFMA2) -> row extreme ->
+//                       P' = f(D) * 2^E (E folded into the ex2 argument, max_j P' in [2^14, 2^15))
+//                       -> fp16 hi/lo pair -> tcgen05.st over S -> drain the warpgroup's previous O
+//                       buffer: acc += O * 2^-E / s_V with round-to-nearest FFMA2 (the tensor core
+//                       accumulates with truncation, so every sub-tile gets a fresh accumulator)
 //
 // Split-precision arithmetic (why fp32 parity holds, DESIGN.md "numerics"):
 //   x*s = hi + lo (+2^-22), fp16 pair, s a power of two chosen per operand so |x*s| < 2^13
-//   P   = hi + lo (+2^-21), tf32 pair;  V likewise
+//   P*2^E and V*s_V likewise (per row and sub-tile / per 64-row V tile power-of-two scales)
 // K is never written to HBM; S and P never leave TMEM / registers.
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -977,6 +977,21 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
         if (splits < 1) splits = 1;
     }
     int64_t tps = (pl->sub_tiles + splits - 1) / splits;
+    {
+        // Multi-wave launches: cap the sub-tiles one CTA sweeps so that all row blocks visit an L2-sized
+        // column chunk (about 48 MB of tile images) before the grid moves on -- blockIdx.z is the
+        // slowest-varying index of the launch order.  Cuts DRAM re-reads of the column panel from ~1000x to
+        // ~20x the algorithmic bytes at C2 (+3 % under the power cap) for splits x n x k floats of workspace.
+        const size_t tile_bytes = tc_image_bytes(kb) + (size_t)kp * 256;
+        int64_t cap = tc_env_int("RLAOPT_B200_TC_SPLIT_TILES", -1);
+        if (cap < 0) cap = (int64_t)((48u << 20) / tile_bytes);
+        if (cap > 0 && base >= target && (size_t)pl->sub_tiles * tile_bytes > ((size_t)64 << 20)) {
+            if (cap < TC_MIN_SPLIT_TILES) cap = TC_MIN_SPLIT_TILES;
+            const int64_t floor_tps = (pl->sub_tiles + 31) / 32;  // at most 32 partial buffers
+            if (cap < floor_tps) cap = floor_tps;
+            if (cap < tps) tps = cap;
+        }
+    }
     splits = (pl->sub_tiles + tps - 1) / tps;
     pl->splits = (int)splits;
     pl->tiles_per_split = (int)tps;

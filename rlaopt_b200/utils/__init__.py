@@ -1,5 +1,7 @@
-"""Host-side helpers (validators) for the kernel-matmat path."""
+"""Host-side helpers (validators, logger, reproducible random draws)."""
 from .input_checkers import *  # noqa: F401,F403
 from . import input_checkers as _ic
+from .logger import Logger
+from .rng import host_rng, host_rng_enabled, randn
 
-__all__ = list(_ic.__all__)
+__all__ = list(_ic.__all__) + ["Logger", "host_rng", "host_rng_enabled", "randn"]

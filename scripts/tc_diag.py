@@ -143,6 +143,70 @@ if __name__ == "__main__":
             print(f"   MMA2 warp clk/tile:", {nm: round(buf[24 + i] / tiles, 1) for i, nm in enumerate(names_m)}, "total", round(sum(buf[24:32]) / tiles, 1), flush=True)
             for base, nm in ((8, "epi warp0"), (16, "epi warp4")):
                 print(f"   {nm} clk per own tile:", {x: round(buf[base + i] / (tiles / 2), 1) for i, x in enumerate(names_e)}, "total", round(sum(buf[base:base + 8]) / (tiles / 2), 1), flush=True)
+    elif which == "sustain":
+        # power-limited regime: ~4 s of back-to-back launches per knock-out, throughput over the last half
+        import subprocess
+        from rlaopt_b200.kernels import KernelConfig, RBFLinOp
+        n, d, k = 262144, 128, 64
+        X = (rnd((n, d), 1) / d**0.5).to(dev)
+        V = rnd((n, k), 2).to(dev)
+        op = RBFLinOp(X, X, KernelConfig(lengthscale=1.0))
+        for diag in (sys.argv[2:] or ["0", "8", "2", "4", "1"]):
+            os.environ["RLAOPT_B200_TC_DIAG"] = diag
+            Y = op @ V
+            torch.cuda.synchronize()
+            reps = 30
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps + 1)]
+            ev[0].record()
+            for i in range(2 * reps):
+                Y = op @ V
+                ev[i + 1].record()
+            smi = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
+            torch.cuda.synchronize()
+            ms = ev[reps].elapsed_time(ev[2 * reps]) / reps
+            print(f"sustain diag {diag}: {ms:.2f} ms  {n*n/ms/1e6:.1f} Gentries/s  [{smi}]", flush=True)
+    elif which == "kinds":
+        # throughput of every kernel family at the C3 shape (d=32, k=16) and the C2 shape, one GPU
+        from rlaopt_b200 import kernels as K
+        from rlaopt_b200.kernels import KernelConfig
+        for name, n, d, k in (("LaplaceLinOp", 131072, 32, 16), ("Matern12LinOp", 131072, 32, 16), ("Matern32LinOp", 262144, 32, 16),
+                              ("Matern52LinOp", 262144, 32, 16), ("RBFLinOp", 262144, 32, 16), ("LaplaceLinOp", 65536, 128, 64),
+                              ("RBFLinOp", 131072, 64, 128), ("RBFLinOp", 131072, 64, 1000), ("RBFLinOp", 131072, 16, 1), ("RBFLinOp", 131072, 8, 10)):
+            X = (rnd((n, d), 1) / d**0.5).to(dev)
+            V = rnd((n, k), 2).to(dev)
+            op = getattr(K, name)(X, X, KernelConfig(lengthscale=1.0))
+            for _ in range(2):
+                Y = op @ V
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                Y = op @ V
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            print(f"{name} n={n} d={d} k={k}: {ms:.2f} ms  {n*n/ms/1e6:.1f} Gentries/s", flush=True)
+    elif which == "l2chunk":
+        # column-chunked launch order: DRAM traffic vs L2-sized chunks, power-limited regime
+        import subprocess
+        from rlaopt_b200.kernels import KernelConfig, RBFLinOp
+        n, d, k = 524288, 128, 64
+        X = (rnd((n, d), 1) / d**0.5).to(dev)
+        V = rnd((n, k), 2).to(dev)
+        for cap in (sys.argv[2:] or ["0", "2048", "1024", "512", "256"]):
+            os.environ["RLAOPT_B200_TC_SPLIT_TILES"] = cap
+            op = RBFLinOp(X, X, KernelConfig(lengthscale=1.0))
+            Y = op @ V
+            torch.cuda.synchronize()
+            reps = 8
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps + 1)]
+            ev[0].record()
+            for i in range(2 * reps):
+                Y = op @ V
+                ev[i + 1].record()
+            torch.cuda.synchronize()
+            ms = ev[reps].elapsed_time(ev[2 * reps]) / reps
+            print(f"split cap {cap}: {ms:.2f} ms  {n*n/ms/1e6:.1f} Gentries/s checksum {float(Y.double().abs().sum()):.6e}", flush=True)
     elif which == "range":
         # tiny kernel values (far-apart clusters): the per-row power-of-two scale keeps relative accuracy
         for shift in (0.0, 0.5, 1.0, 1.5):

@@ -1,7 +1,7 @@
 """tcgen05 tensor-core path (layout = TC) against the fp64 oracle and against the CUDA-core path.
 
 The TC kernel evaluates the L2 kernels in GEMM form with split-precision tensor-core
-products (fp16 hi/lo for X.Y^T, tf32 hi/lo for P.V) and fp32 accumulation; the bar is
+products (fp16 hi/lo pairs for X.Y^T and for P.V, with exact power-of-two scales) and fp32 accumulation; the bar is
 the same 1e-5 relative Frobenius error as the CUDA-core kernel (BASELINE north_star).
 """
 import pytest
@@ -116,3 +116,82 @@ def test_tc_deterministic(dev):
     a = kernel_matmat(X, X, V, "matern32", 1.0, layout=LAYOUT_TC)
     b = kernel_matmat(X, X, V, "matern32", 1.0, layout=LAYOUT_TC)
     assert torch.equal(a, b)
+
+
+def test_wide_dynamic_range_v(dev):
+    """V tiles carry their own power-of-two scale: rows of V spanning 24 orders of magnitude."""
+    from rlaopt_b200._lib import LAYOUT_TC
+    from rlaopt_b200.ops import kernel_matmat
+
+    n, m, d, k = 512, 4096, 64, 32
+    A1, A2 = _rand((n, d), 15) / d**0.5, _rand((m, d), 16) / d**0.5
+    V = _rand((m, k), 17) * torch.logspace(-12, 12, m).unsqueeze(1)
+    ref = ko.kernel_matmat_gemm_form(A1, A2, V, "rbf", 1.0, dtype=torch.float64)
+    got = kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), "rbf", 1.0, layout=LAYOUT_TC)
+    assert ko.rel_fro_error(got, ref) <= 1e-5
+    # tiny and huge V as a whole (scale is exact, results scale exactly)
+    V1 = _rand((m, k), 18)
+    base = kernel_matmat(A1.to(dev), A2.to(dev), V1.to(dev), "matern52", 1.0, layout=LAYOUT_TC)
+    for e in (-100, -30, 40, 100):
+        got = kernel_matmat(A1.to(dev), A2.to(dev), (V1 * 2.0**e).to(dev), "matern52", 1.0, layout=LAYOUT_TC)
+        assert torch.equal(got, base * 2.0**e), e
+
+
+@pytest.mark.parametrize("name", TC_KERNELS)
+def test_tiny_kernel_values_keep_relative_accuracy(dev, name):
+    """Far-apart clusters: every K_ij is tiny (down to 1e-27 for RBF).  P is scaled per row and
+    sub-tile before the fp16 split, so the result keeps its relative accuracy instead of flushing."""
+    from rlaopt_b200._lib import LAYOUT_TC
+    from rlaopt_b200.ops import kernel_matmat
+
+    n, m, d, k = 384, 4096, 64, 32
+    A1 = _rand((n, d), 19) / d**0.5
+    V = _rand((m, k), 20)
+    for shift in (0.5, 1.0, 1.5):
+        A2 = _rand((m, d), 21) / d**0.5 + shift
+        ref = ko.kernel_matmat_gemm_form(A1, A2, V, name, 1.0, dtype=torch.float64)
+        assert ref.abs().max() > 0
+        got = kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), name, 1.0, layout=LAYOUT_TC)
+        assert ko.rel_fro_error(got, ref) <= 1e-5, (name, shift, float(ref.abs().max()))
+
+
+def test_mixed_magnitudes_within_a_row(dev):
+    """One near-duplicate column (K = 1) among far columns (K ~ 1e-9) in the same 64-column sub-tile,
+    with V weighting the far columns up: the small entries must not be lost next to the large one."""
+    from rlaopt_b200._lib import LAYOUT_TC
+    from rlaopt_b200.ops import kernel_matmat
+
+    n, m, d, k = 256, 1024, 16, 4
+    A1 = _rand((n, d), 22) / d**0.5
+    A2 = _rand((m, d), 23) / d**0.5 + 1.5
+    A2[::64] = A1[: m // 64] + 1e-3  # one close point per sub-tile for the first rows
+    V = _rand((m, k), 24)
+    V[::64] *= 1e-6
+    ref = ko.kernel_matmat_gemm_form(A1, A2, V, "rbf", 1.0, dtype=torch.float64)
+    got = kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), "rbf", 1.0, layout=LAYOUT_TC)
+    assert ko.rel_fro_error(got, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("m", [64, 65, 128, 129, 192, 64 * 17, 64 * 33 + 1, 40000])
+def test_odd_and_even_sub_tile_counts(dev, m):
+    """The two epilogue warpgroups alternate over the 64-column sub-tiles; cover 1, 2, 3 ... tiles,
+    ragged last tiles and the split-column path whose last split holds a single tile."""
+    from rlaopt_b200._lib import LAYOUT_TC
+    from rlaopt_b200.ops import kernel_matmat
+
+    n, d, k = 70, 50, 7
+    A1, A2, V = _rand((n, d), 25) / d**0.5, _rand((m, d), 26) / d**0.5, _rand((m, k), 27)
+    ref = ko.kernel_matmat_gemm_form(A1, A2, V, "rbf", 1.0, dtype=torch.float64)
+    got = kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), "rbf", 1.0, layout=LAYOUT_TC)
+    assert ko.rel_fro_error(got, ref) <= 1e-5, m
+
+
+def test_k_chunks_and_wide_features(dev):
+    from rlaopt_b200._lib import LAYOUT_TC
+    from rlaopt_b200.ops import kernel_matmat
+
+    for n, m, d, k in ((300, 2000, 64, 200), (257, 1500, 192, 65), (130, 700, 129, 1), (500, 900, 16, 1000)):
+        A1, A2, V = _rand((n, d), 28) / d**0.5, _rand((m, d), 29) / d**0.5, _rand((m, k), 30)
+        ref = ko.kernel_matmat_gemm_form(A1, A2, V, "matern32", 1.3, dtype=torch.float64)
+        got = kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), "matern32", 1.3, layout=LAYOUT_TC)
+        assert ko.rel_fro_error(got, ref) <= 1e-5, (n, m, d, k)
