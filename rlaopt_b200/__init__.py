@@ -9,5 +9,6 @@ import torch  # noqa: F401  (device memory, streams, torch.distributed plumbing)
 
 from . import ops  # registers torch.ops.rlaopt_b200.kernel_matmat  # noqa: F401
 from . import linops, kernels  # noqa: F401
+from . import sketches, preconditioners, spectral_estimators, solvers, models  # noqa: F401  consumers of the path
 
 __version__ = "0.1.0"

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256) tc_pack_v_kernel(const float* __restrict_
     for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
     int E = 0;
     if (mx > 0.0f) E = 14 - ilogbf(mx);
-    E = max(-100, min(100, E));
+    E = max(-126, min(126, E));
     const float s = __uint_as_float((uint32_t)(127 + E) << 23);
     const size_t image_bytes = (size_t)kp * 256 + 16;
     unsigned char* img = images + ((size_t)kc * sub_tiles + t) * image_bytes;

@@ -1,0 +1,118 @@
+"""KRR solves on the GPU through the fused kernel operators, against the iterates of the reference's own
+solvers (tests/golden/solvers_ref_*.pt): PCG with Nystrom / identity preconditioners and SAP / ASkotch with
+row and block oracles.  Random draws come from the seeded CPU stream (rlaopt_b200.utils.host_rng), so the
+sketch matrices, power-iteration starts and coordinate blocks are the ones the reference run used.
+"""
+import pytest
+import torch
+
+from solver_cases import Recorder, kernel_linsys, load_cases, solver_config_for
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["pcg_nystrom_gauss_rbf", "pcg_identity_matern52", "pcg_nystrom_ortho_rbf_k1", "askotch_nystrom_gauss_rbf",
+         "sap_identity_laplace"]
+
+
+def _solve(case, dtype, rtol):
+    from rlaopt_b200.utils import host_rng
+
+    dev = torch.device("cuda:0")
+    case = dict(case)
+    case["X"], case["B"] = case["X"].to(dtype), case["B"].to(dtype)
+    system = kernel_linsys(case, dev)
+    rec = Recorder()
+    unhook = rec.hook()
+    torch.manual_seed(case["seed"] + 1)
+    try:
+        with host_rng():
+            W, log = system.solve(solver_config_for(case["name"], dev, rtol),
+                                  torch.zeros(case["n"], case["k"], dtype=dtype, device=dev), callback_fn=rec,
+                                  callback_freq=case["callback_freq"])
+    finally:
+        unhook()
+    return W.cpu(), log, rec
+
+
+def _check(case, W, log, rec, early_iters, early_tol, final_tol, count_slack):
+    """Parity with the reference run of the same seeded problem.
+
+    Krylov recurrences amplify rounding differences exponentially (a 1e-14 perturbation of the first matmat is
+    O(1) after ~10 unpreconditioned CG steps), so "same iterates" is asserted on the
+    first iterations, "same answer" on the converged solutions, and the iteration count up to `count_slack`
+    logging periods.
+    """
+    iters = sorted(log)
+    ref_iters = case["logged_iters"]
+    freq = case["callback_freq"]
+    assert abs(iters[-1] - ref_iters[-1]) <= count_slack * freq, (iters[-1], ref_iters[-1])
+    rel = torch.stack([log[i]["metrics"]["internal_metrics"]["rel_res"].cpu() for i in iters])
+    n_early = min(early_iters // freq + 1, len(iters), len(ref_iters))
+    assert torch.allclose(rel[:n_early], case["rel_res"][:n_early], rtol=early_tol * 10, atol=0.0), (rel[:n_early], case["rel_res"][:n_early])
+    for i, W_ref in case["W_at"].items():
+        if i <= early_iters and i in iters:
+            got = rec.W[iters.index(i)].cpu()
+            assert torch.linalg.norm(got - W_ref) <= early_tol * torch.linalg.norm(W_ref), (case["name"], i)
+    return iters, rel
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fp32_solves_match_reference(name):
+    case = load_cases("float32")[name]
+    W, log, rec = _solve(case, torch.float32, 1e-4)
+    pcg = name.startswith("pcg")
+    iters, rel = _check(case, W, log, rec, early_iters=3 if pcg else 60, early_tol=2e-4 if pcg else 2e-3,
+                        final_tol=None, count_slack=2 if pcg else 0)
+    if pcg:  # converged: same answer, residual below the tolerance
+        assert bool((rel[-1] <= 1e-4).all())
+        assert torch.linalg.norm(W - case["W_final"]) <= 1e-4 * torch.linalg.norm(case["W_final"])
+    else:  # SAP / ASkotch: fixed number of block steps, identical blocks, same trajectory
+        assert torch.equal(torch.stack(rec.blocks), case["blocks"])
+        assert torch.allclose(torch.tensor(rec.steps, dtype=torch.float64), case["steps"], rtol=1e-3)
+        assert torch.allclose(rel, case["rel_res"], rtol=1e-3)
+        assert torch.linalg.norm(W - case["W_final"]) <= 2e-3 * torch.linalg.norm(case["W_final"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fp64_solves_match_reference(name):
+    case = load_cases("float64")[name]
+    W, log, rec = _solve(case, torch.float64, 1e-9)
+    pcg = name.startswith("pcg")
+    iters, rel = _check(case, W, log, rec, early_iters=5 if pcg else 60, early_tol=1e-9 if pcg else 1e-8,
+                        final_tol=None, count_slack=2 if pcg else 0)
+    if pcg:
+        assert bool((rel[-1] <= 1e-9).all())
+        assert torch.linalg.norm(W - case["W_final"]) <= 1e-8 * torch.linalg.norm(case["W_final"])
+    else:
+        assert torch.equal(torch.stack(rec.blocks), case["blocks"])
+        assert torch.allclose(torch.tensor(rec.steps, dtype=torch.float64), case["steps"], rtol=1e-8)
+        assert torch.allclose(rel, case["rel_res"], rtol=1e-8)
+        assert torch.linalg.norm(W - case["W_final"]) <= 1e-8 * torch.linalg.norm(case["W_final"])
+
+
+def test_krr_pcg_config1_shape():
+    """BASELINE configs[0] shape (RBF KRR n = 20k, d = 8, Nystrom rank 200, reg = 1, fp32): converges to rtol 1e-4
+    and agrees with a dense fp64 solve on a row sample of the normal equations."""
+    from oracle import kernel_oracle as ko
+    from rlaopt_b200.kernels import KernelConfig, RBFLinOp
+    from rlaopt_b200.models import LinSys
+    from rlaopt_b200.preconditioners import NystromConfig
+    from rlaopt_b200.solvers import PCGConfig
+
+    dev = torch.device("cuda:0")
+    n, d, k = 20000, 8, 2
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(n, d, generator=g) / d**0.5
+    B = torch.randn(n, k, generator=g)
+    A = RBFLinOp(X.to(dev), X.to(dev), KernelConfig(lengthscale=1.0))
+    system = LinSys(A, B.to(dev), reg=1.0)
+    torch.manual_seed(1)
+    W, log = system.solve(PCGConfig(device=dev, max_iters=100, rtol=1e-4,
+                                    precond_config=NystromConfig(rank=200, rho=1.0, sketch="gauss")),
+                          torch.zeros(n, k, device=dev), callback_freq=1)
+    assert max(log) < 40
+    assert bool((log[max(log)]["metrics"]["internal_metrics"]["rel_res"] <= 1e-4).all())
+    rows = torch.arange(0, n, 40)
+    KW = ko.kernel_matmat(X, X, W.cpu().double(), "rbf", 1.0, row_idx=rows, dtype=torch.float64)
+    res = B[rows].double() - (KW + 1.0 * W.cpu().double()[rows])
+    assert torch.linalg.norm(res) <= 3e-4 * torch.linalg.norm(B[rows].double())
