@@ -179,6 +179,19 @@ def run_reference(args) -> int:
         "e2e": {"value": value, "unit": "Gentries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_krr:
+        from oracle import kernel_oracle as ko
+        from rlaopt_b200.linops import SymmetricLinOp
+
+        cpu = torch.device("cpu")
+
+        def oracle_op(Xc):
+            nn = Xc.shape[0]
+            mm = lambda Vc: ko.kernel_matmat_gemm_form(Xc, Xc, Vc, "rbf", 1.0)
+            return SymmetricLinOp(cpu, torch.Size((nn, nn)), mm, mm, dtype=torch.float32)
+
+        line["krr_pcg"] = krr_pcg_solve(cpu, oracle_op, reps=0)
+        line["krr_pcg"]["note"] = "reference solver arithmetic (PCG + Nystrom) on the CPU over the oracle's torch kernel operator"
     print(json.dumps(line), flush=True)
     return 0
 
@@ -190,6 +203,44 @@ def _config(workload, kernel, n, d, k, gpus):
         "parallelism": f"row-partition x{gpus} (A2, V replicated; all-gather of row blocks)" if gpus > 1 else "single GPU",
         "l2": "inputs (X+V) exceed the 126 MB L2; no flush between iterations",
     }
+
+
+# ----------------------------------------------------------------------------- KRR PCG solve (BASELINE configs[0])
+C1 = {"n": 20_000, "d": 8, "k": 1, "rank": 200, "reg": 1.0, "rtol": 1e-4, "max_iters": 100}
+
+
+def krr_pcg_solve(device, linop_factory, reps: int = 1) -> dict:
+    """Nystrom-preconditioned PCG on the C1 problem (RBF KRR, n = 20k, d = 8, rank 200, fp32):
+    wall seconds of LinSys.solve (operator construction, sketch, preconditioner build, iterations, residual
+    checks at callback_freq = 1), random draws on the seeded CPU stream so both arms see the same Omega."""
+    from rlaopt_b200.models import LinSys
+    from rlaopt_b200.preconditioners import NystromConfig
+    from rlaopt_b200.solvers import PCGConfig
+    from rlaopt_b200.utils import host_rng
+
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(C1["n"], C1["d"], generator=g) / C1["d"] ** 0.5
+    B = torch.randn(C1["n"], C1["k"], generator=g)
+    best, iters, rel = None, None, None
+    for _ in range(reps + 1):  # first pass warms allocator / cuSOLVER handles
+        torch.manual_seed(1)
+        if device.type == "cuda":
+            torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        A = linop_factory(X.to(device))
+        system = LinSys(A, B.to(device), reg=C1["reg"])
+        cfg = PCGConfig(device=device, max_iters=C1["max_iters"], rtol=C1["rtol"],
+                        precond_config=NystromConfig(rank=C1["rank"], rho=C1["reg"], sketch="gauss"))
+        with host_rng():
+            W, log = system.solve(cfg, torch.zeros(C1["n"], C1["k"], device=device), callback_freq=1)
+        if device.type == "cuda":
+            torch.cuda.synchronize(device)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        iters = max(log)
+        rel = float(log[iters]["metrics"]["internal_metrics"]["rel_res"].max())
+    return {"seconds": best, "iterations": iters, "rel_res": rel, "unit": "s",
+            "config": "RBF KRR n=20000 d=8 k=1, Nystrom rank 200 (gauss), reg=1.0, rtol=1e-4, fp32, callback_freq=1"}
 
 
 # ----------------------------------------------------------------------------- ours
@@ -352,6 +403,12 @@ def run_ours(args) -> int:
         base = cpu_baseline(kernel, X, V, budget_s=args.ref_budget_s)
         base.pop("seconds", None)
         line["cpu_baseline"] = base
+    if world == 1 and not args.no_krr:
+        from rlaopt_b200.kernels import RBFLinOp
+
+        del op, Y, Vg
+        torch.cuda.empty_cache()
+        line["krr_pcg"] = krr_pcg_solve(dev, lambda Xd: RBFLinOp(Xd, Xd, cfg), reps=2)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -368,6 +425,7 @@ def main() -> int:
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--ref-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-krr", action="store_true", help="skip the secondary KRR PCG solve (BASELINE configs[0])")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
