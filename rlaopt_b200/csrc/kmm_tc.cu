@@ -148,6 +148,30 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// CTA-pair variants: the copy lands at the same smem offset in every CTA of `mask` and signals the mbarrier at the
+// same offset in each of them; the commit arrives on the barrier at that offset in every CTA of `mask`
+__device__ __forceinline__ void bulk_copy_g2s_mc(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                                 uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -375,6 +399,7 @@ struct TcParams {
     int k, kb, nk1, kid;
     int a_stages, v_stages;  // smem ring depths (column-tile images / V images + norms)
     int nb, la;              // S/P buffers in TMEM, MMA1 look-ahead (tiles)
+    int pair;                // 1: launched as clusters of two CTAs that share every column-tile load (multicast halves)
     int diag;                // RLAOPT_B200_TC_DIAG knock-outs (profiling only): 1 no MMA, 2 no pointwise, 4 no drain, 8 no loads
     float scale_out;
     int64_t sub_tiles;        // ceil(m / 64)
@@ -459,13 +484,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
     const int T = (int)(t_end - t_begin);
 
     if (threadIdx.x == 0) {
+        const uint32_t consumers = p.pair ? 2 : 1;  // a ring slot is free once both CTAs of the pair have read it
         for (int s = 0; s < SA; ++s) {
             mbar_init(&a_full[s], 1);
-            mbar_init(&a_empty[s], 1);
+            mbar_init(&a_empty[s], consumers);
         }
         for (int s = 0; s < SV; ++s) {
             mbar_init(&v_full[s], 1);
-            mbar_init(&v_empty[s], 1);
+            mbar_init(&v_empty[s], consumers);
         }
         for (int b = 0; b < NB; ++b) {
             mbar_init(&s_full[b], 1);
@@ -482,6 +508,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
     if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
+    if (p.pair) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t col_a_hi = 0, col_a_lo = KB * 32, col_sp = KB * 64, col_o = KB * 64 + NB * 64;
@@ -502,6 +529,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             const float* n_src = col_norms + t_begin * TC_BN;
             int sa = 0, sv = 0;
             uint32_t pha = 1, phv = 1;  // a fresh barrier passes a wait on parity 1
+            const uint32_t crank = p.pair ? cluster_ctarank() : 0;
             for (int u = 0; u < T; ++u) {
                 mbar_wait(&a_empty[sa], pha);
                 if (p.diag & 8) {
@@ -509,13 +537,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
                     mbar_wait(&v_empty[sv], phv);
                     mbar_arrive(&v_full[sv]);
                 } else {
-                mbar_arrive_expect_tx(&a_full[sa], a_img_bytes);
-                bulk_copy_g2s(a_ring + (size_t)sa * a_img_bytes, a_src, a_img_bytes, &a_full[sa]);
-                mbar_wait(&v_empty[sv], phv);
-                unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
-                mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
-                bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
-                bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
+                if (!p.pair) {
+                    mbar_arrive_expect_tx(&a_full[sa], a_img_bytes);
+                    bulk_copy_g2s(a_ring + (size_t)sa * a_img_bytes, a_src, a_img_bytes, &a_full[sa]);
+                    mbar_wait(&v_empty[sv], phv);
+                    unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
+                    mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
+                    bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
+                    bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
+                } else {
+                    // each CTA of the pair fetches half of every image and multicasts it to both
+                    const uint32_t a_half = a_img_bytes / 2;
+                    mbar_arrive_expect_tx(&a_full[sa], a_img_bytes);
+                    bulk_copy_g2s_mc(a_ring + (size_t)sa * a_img_bytes + crank * a_half, a_src + crank * a_half, a_half,
+                                     &a_full[sa], 3);
+                    mbar_wait(&v_empty[sv], phv);
+                    unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
+                    mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
+                    constexpr uint32_t v_half = KP * 128;
+                    if (crank == 0) {
+                        bulk_copy_g2s_mc(vdst, v_src, v_half, &v_full[sv], 3);
+                        bulk_copy_g2s_mc(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv], 3);
+                    } else {
+                        bulk_copy_g2s_mc(vdst + v_half, v_src + v_half, v_half + 16, &v_full[sv], 3);
+                    }
+                }
                 }
                 a_src += a_img_bytes;
                 v_src += v_img_bytes;
@@ -615,7 +661,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
                 issue_mma1(b1, sa);
                 if (elect_one()) {
                     umma_commit(&s_full[b1]);
-                    umma_commit(&a_empty[sa]);
+                    if (p.pair) umma_commit_mc(&a_empty[sa], 3);
+                    else umma_commit(&a_empty[sa]);
                 }
                 __syncwarp();
                 TC_PROF(2)
@@ -645,7 +692,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
                 tc_fence_after();
                 issue_mma2(b2, ob, sv);
                 if (elect_one()) {
-                    umma_commit(&v_empty[sv]);
+                    if (p.pair) umma_commit_mc(&v_empty[sv], 3);
+                    else umma_commit(&v_empty[sv]);
                     umma_commit(&p_free[b2]);
                     umma_commit(&o_full[ob]);
                 }
@@ -671,7 +719,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         const int row = q * 32 + lane;
         const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
         const int64_t grow = row0 + row;
-        const float nx = reinterpret_cast<const float*>(p.rows + tc_norm_offset())[grow];
+        const bool live = grow < tc_npad(p.n);  // a pair's second CTA may lie past the last row block (odd count)
+        const float nx = live ? reinterpret_cast<const float*>(p.rows + tc_norm_offset())[grow] : 0.0f;
         const float m2c = -2.0f * rh->inv_scale * ch->inv_scale;
 
         // ---- X tile -> TMEM (h = 0: hi halves, h = 1: lo halves) ----
@@ -683,8 +732,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
                 uint32_t w[32];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(img + (size_t)kb * TC_KBLOCK_BYTES + (size_t)r * 128 +
-                                                                    (size_t)((c ^ (r & 7)) * 16));
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (live)
+                        v = *reinterpret_cast<const uint4*>(img + (size_t)kb * TC_KBLOCK_BYTES + (size_t)r * 128 +
+                                                            (size_t)((c ^ (r & 7)) * 16));
                     w[c * 4 + 0] = v.x;
                     w[c * 4 + 1] = v.y;
                     w[c * 4 + 2] = v.z;
@@ -924,11 +975,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
 
     tc_fence_before();
     __syncthreads();
+    if (p.pair) cluster_sync_all();  // no CTA leaves while its peer can still multicast into it or signal its barriers
     if (warp == TC_EPI_WARPS) tmem_dealloc(tmem, 512);
 }
 
 struct TcPlan {
-    int kb, kp, k_chunks, a_stages, v_stages, nb, la, splits, tiles_per_split;
+    int kb, kp, k_chunks, a_stages, v_stages, nb, la, splits, tiles_per_split, pair;
     int64_t sub_tiles;
     size_t smem_bytes, vimg_bytes, part_bytes;
 };
@@ -966,6 +1018,13 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     pl->nb = nb;
     pl->la = la;
     pl->sub_tiles = (m + TC_BN - 1) / TC_BN;
+    // CTA pairs (clusters of two row blocks sharing every column-tile load through multicast): +3 % under the
+    // power cap at C2.  Default: on once the launch has at least two waves of row blocks; RLAOPT_B200_TC_PAIR=0/1 forces.
+    {
+        const int64_t row_blocks = (n + TC_BM - 1) / TC_BM;
+        const int want = tc_env_int("RLAOPT_B200_TC_PAIR", -1);
+        pl->pair = row_blocks >= 2 && (want < 0 ? row_blocks >= 2 * (int64_t)sm_count : want != 0);
+    }
     pl->smem_bytes = sa * a_stage + sv * v_stage + fixed;
     const int64_t base = ((n + TC_BM - 1) / TC_BM) * pl->k_chunks;
     const int64_t target = (int64_t)sm_count * 2;
@@ -1041,9 +1100,21 @@ static cudaError_t launch_tc_kp(const TcParams& p, const TcPlan& pl, int64_t n, 
     auto kern = kmm_tc_kernel<KP>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (err != cudaSuccess) return err;
-    dim3 grid((unsigned)((n + TC_BM - 1) / TC_BM), (unsigned)pl.k_chunks, (unsigned)pl.splits);
-    kern<<<grid, TC_THREADS, pl.smem_bytes, stream>>>(p);
-    return cudaGetLastError();
+    unsigned row_blocks = (unsigned)((n + TC_BM - 1) / TC_BM);
+    if (p.pair) row_blocks = (row_blocks + 1) & ~1u;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(row_blocks, (unsigned)pl.k_chunks, (unsigned)pl.splits);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.pair ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packed, int64_t m, int64_t d,
@@ -1076,6 +1147,7 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     p.nb = pl.nb;
     p.la = pl.la;
     p.diag = tc_env_int("RLAOPT_B200_TC_DIAG", 0);
+    p.pair = pl.pair;
     p.kid = kid;
     p.sub_tiles = pl.sub_tiles;
     p.tiles_per_split = pl.tiles_per_split;
