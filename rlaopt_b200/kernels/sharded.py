@@ -17,7 +17,26 @@ from rlaopt_b200.linops.spmd import RowShardedLinOp, shard_rows
 from .base import _KernelLinOp
 from .configs import KernelConfig
 
-__all__ = ["sharded_kernel_linop"]
+__all__ = ["sharded_kernel_linop", "replicate_from_host"]
+
+
+def replicate_from_host(T_host: torch.Tensor, device: torch.device,
+                        group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Replica of a (pinned) host matrix on every rank's GPU: each rank copies 1/world of the rows over
+    PCIe and the blocks are all-gathered over NVLink, instead of every rank pulling the whole matrix
+    through the host link (``rlaopt/kernels/base.py:143-144`` moves the full A2 to every device)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return T_host.to(device, non_blocking=True)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = T_host.shape[0]
+    block = -(-n // world)
+    full = torch.empty((block * world,) + tuple(T_host.shape[1:]), dtype=T_host.dtype, device=device)
+    lo, hi = min(rank * block, n), min((rank + 1) * block, n)
+    mine = full[rank * block:rank * block + (hi - lo)]
+    mine.copy_(T_host[lo:hi], non_blocking=True)
+    # in-place all-gather: this rank's block already sits at its slot of the output (ragged tails are padding)
+    dist.all_gather_into_tensor(full, full[rank * block:(rank + 1) * block], group=group)
+    return full[:n]
 
 
 def sharded_kernel_linop(

@@ -20,6 +20,7 @@ from rlaopt_b200.linops import LinOp
 from rlaopt_b200.preconditioners import (IdentityConfig, NewtonConfig, NystromConfig, Preconditioner,
                                          PreconditionerConfig, _get_precond)
 from rlaopt_b200.spectral_estimators import randomized_powering
+from rlaopt_b200.utils import sync_from_rank0
 
 from ._configs import SAPAccelConfig
 from ._solver import Solver
@@ -60,12 +61,13 @@ class SAP(Solver):
     # ---- pieces of one step ----
     def _get_blk(self) -> torch.Tensor:
         try:
-            return torch.multinomial(self.probs, self.blk_sz, replacement=False)
+            blk = torch.multinomial(self.probs, self.blk_sz, replacement=False)
         except RuntimeError as err:  # more than 2^24 categories
             if "number of categories cannot exceed" not in str(err):
                 raise
             pick = np.random.choice(self.probs.shape[0], size=self.blk_sz, replace=False, p=self.probs_cpu)
-            return torch.from_numpy(pick)
+            blk = torch.from_numpy(pick)
+        return sync_from_rank0(blk, self.device)  # SPMD runs: every rank works on rank 0's block
 
     def _get_precond(self, blk: torch.Tensor, A_bb=None) -> Preconditioner:
         P = _get_precond(self.precond_config)

@@ -57,6 +57,11 @@ def _worker(rank, world, port, n, m, out):
         gram = V.new_zeros(3, 3) if hi == lo else W[lo:hi].T @ P
         dist.all_reduce(gram)
         ok &= torch.allclose(gram, W.T @ (Kd @ V), atol=1e-4)
+        # host -> every rank replication (1/world of the rows per rank, then all-gather), ragged n included
+        from rlaopt_b200.kernels.sharded import replicate_from_host
+
+        ok &= torch.equal(replicate_from_host(A1, torch.device("cpu")), A1)
+        ok &= torch.equal(replicate_from_host(V[:, 0].contiguous(), torch.device("cpu")), V[:, 0])
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
@@ -69,3 +74,69 @@ def test_row_sharded_operator_gloo(world, n, m):
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, n, m, out), nprocs=world, join=True)
         assert dict(out) == {r: True for r in range(world)}
+
+
+def _solver_worker(rank, world, port, out):
+    """KRR solves with replicated solver state over the row-sharded operator: different local seeds on the two
+    ranks, random draws taken from rank 0 (replicated_rng) -> identical iterates, equal to a one-process solve."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import kernel_oracle as ko
+        from rlaopt_b200.linops import LinOp, SymmetricLinOp, TwoSidedLinOp
+        from rlaopt_b200.linops.spmd import RowShardedLinOp, shard_rows
+        from rlaopt_b200.models import LinSys
+        from rlaopt_b200.preconditioners import NystromConfig
+        from rlaopt_b200.solvers import PCGConfig, SAPAccelConfig, SAPConfig
+        from rlaopt_b200.utils import replicated_rng
+
+        cpu = torch.device("cpu")
+        g = torch.Generator().manual_seed(0)
+        n, k = 400, 2
+        X = torch.randn(n, 5, generator=g, dtype=torch.float64) / 5**0.5
+        B = torch.randn(n, k, generator=g, dtype=torch.float64)
+        K = ko.kernel_matrix(X, X, "rbf", 1.0, dtype=torch.float64)
+        lo, hi = shard_rows(n, world)[rank]
+        Kr = K[lo:hi]
+        local = TwoSidedLinOp(cpu, torch.Size(Kr.shape), lambda x: Kr @ x, lambda x: Kr.T @ x, lambda x: Kr @ x,
+                              lambda x: Kr.T @ x, dtype=torch.float64)
+        A = RowShardedLinOp(local, torch.Size((n, n)), cpu, torch.float64)
+
+        def row_oracle(blk):  # sharded over the columns would need a reduce; rows of K are cheap here
+            Kb = K[blk]
+            return LinOp(cpu, torch.Size((len(blk), n)), lambda v: Kb @ v, lambda V: Kb @ V, dtype=torch.float64)
+
+        def blk_oracle(blk):
+            Kbb = K[blk][:, blk]
+            return LinOp(cpu, torch.Size((len(blk), len(blk))), lambda v: Kbb @ v, lambda V: Kbb @ V, dtype=torch.float64)
+
+        torch.manual_seed(1234 + rank)  # deliberately different local streams
+        ok = True
+        with replicated_rng():
+            W, log = LinSys(A, B, reg=0.3).solve(
+                PCGConfig(device=cpu, max_iters=60, rtol=1e-10, precond_config=NystromConfig(rank=40, rho=0.3, sketch="gauss")),
+                torch.zeros(n, k, dtype=torch.float64), callback_freq=1)
+            W2, _ = LinSys(A, B, reg=0.3, A_row_oracle=row_oracle, A_blk_oracle=blk_oracle).solve(
+                SAPConfig(device=cpu, max_iters=30, rtol=1e-10, blk_sz=50, precond_config=NystromConfig(rank=20, rho=0.3),
+                          accel_config=SAPAccelConfig(mu=0.3, nu=3.0)), torch.zeros(n, k, dtype=torch.float64), callback_freq=10)
+        ref = torch.linalg.solve(K + 0.3 * torch.eye(n, dtype=torch.float64), B)
+        ok &= bool(torch.linalg.norm(W - ref) <= 1e-8 * torch.linalg.norm(ref))
+        # identical iterates on every rank
+        for T in (W, W2):
+            mine = T.clone()
+            other = T.clone()
+            dist.broadcast(other, src=0)
+            ok &= bool(torch.equal(mine, other))
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_spmd_replicated_solvers_world2():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_solver_worker, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
