@@ -358,13 +358,22 @@ def run_ours(args) -> int:
     else:
         peak = ffma_peak
         bound, peak_note = "fp32", f"148 SMs x 128 FFMA lanes x 2 x {sm_max:.0f} MHz ({peaks['_source']} sm_max_mhz)"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if world == 1 and os.path.exists(tpath):
+        with open(tpath) as f:
+            entry = json.load(f).get(args.workload)
+        want = "kmm_tc_kernel" if layout == _lib.LAYOUT_TC else "kmm_simt_kernel"
+        if entry and entry.get("kernel") == want:
+            traffic = entry["traffic_bytes"]  # per launch, from the committed ncu --set full capture
     roofline = {
         "bound": bound,
         "achieved": achieved,
         "peak": peak,
         "unit": "TFLOP/s",
         "frac": achieved / peak,
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
         "kernel": "kmm_tc_kernel" if layout == _lib.LAYOUT_TC else "kmm_simt_kernel",
         "peak_note": peak_note,
         "ffma_peak_tflops": ffma_peak,

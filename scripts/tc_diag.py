@@ -123,12 +123,15 @@ if __name__ == "__main__":
     elif which == "prof2":
         # per-section cycle counters of CTA 0 (needs the -DKMM_TC_PROFILE build, RLAOPT_B200_LIB=...)
         import ctypes
-        from rlaopt_b200.kernels import KernelConfig, RBFLinOp
+        from rlaopt_b200.kernels import KernelConfig
         lib = _lib.load()
-        n, d, k = 131072, 128, 64
+        from rlaopt_b200 import kernels as K
+        cls_name = sys.argv[2] if len(sys.argv) > 2 else "RBFLinOp"
+        n, d, k = (int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])) if len(sys.argv) > 5 else (131072, 128, 64)
         X = (rnd((n, d), 1) / d**0.5).to(dev)
         V = rnd((n, k), 2).to(dev)
-        op = RBFLinOp(X, X, KernelConfig(lengthscale=1.0))
+        op = getattr(K, cls_name)(X, X, KernelConfig(lengthscale=1.0))
+        print(cls_name, n, d, k, "NB", os.environ.get("RLAOPT_B200_TC_NB"), flush=True)
         for diag in ("0", "2", "1", "3"):
             os.environ["RLAOPT_B200_TC_DIAG"] = diag
             for _ in range(2):
