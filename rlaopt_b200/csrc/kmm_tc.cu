@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
     unsigned char* a_ring = smem;
     unsigned char* v_ring = smem + (size_t)SA * a_img_bytes;
     float* xchg = reinterpret_cast<float*>(v_ring + (size_t)SV * v_stage_bytes);  // [2][2][128] row-max exchange
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 2 * 2 * TC_BM);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 8 * TC_BM);
     uint64_t* a_full = bars;             // [SA] producer -> MMA1
     uint64_t* a_empty = a_full + SA;     // [SA] MMA1 done -> producer
     uint64_t* v_full = a_empty + SA;     // [SV] producer -> MMA2 / epilogue (norms, V scale)
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&o_full[b], 1);
-            mbar_init(&o_free[b], TC_EPI_WARPS / 2);
+            mbar_init(&o_free[b], KP > 64 ? TC_EPI_WARPS : TC_EPI_WARPS / 2);
         }
         mbar_init(x_full, TC_EPI_WARPS);
         fence_barrier_init();
@@ -754,20 +754,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         // warps that share an SM sub-partition work on different tiles, covering each other's
         // TMEM / MUFU latencies.
         const int g = h;
-        uint64_t acc[KP / 2];  // fp32 pairs: this warpgroup's partial row of Y (KP columns)
+        // KP <= 64: a warpgroup drains the O buffers of its own tiles (all KP columns) and the two partial rows
+        // are added at the end.  KP = 128 (k > 64): both warpgroups drain every tile, half of the columns each,
+        // so a thread still carries 64 accumulators; the owner publishes the tile's scale through smem.
+        constexpr bool SPLIT = KP > 64;
+        constexpr int DW = SPLIT ? KP / 2 : KP;  // O columns one thread accumulates
+        uint64_t acc[DW / 2];                    // fp32 pairs
 #pragma unroll
-        for (int c = 0; c < KP / 2; ++c) acc[c] = 0ull;
+        for (int c = 0; c < DW / 2; ++c) acc[c] = 0ull;
 
-        // acc += O[g] * dsc: one sub-tile's accumulator, un-scaled and added with round-to-nearest
-        auto drain = [&](uint32_t par, float dsc) {
-            mbar_wait(&o_full[g], par);
+        // acc += O[ob] * dsc: one sub-tile's accumulator, un-scaled and added with round-to-nearest
+        auto drain = [&](int ob, uint32_t par, float dsc) {
+            mbar_wait(&o_full[ob], par);
             tc_fence_after();
             const uint64_t d2 = pack2(dsc, dsc);
 #pragma unroll
-            for (int c0 = 0; c0 < KP; c0 += 32) {
-                constexpr int W = KP < 32 ? KP : 32;
+            for (int c0 = 0; c0 < DW; c0 += 32) {
+                constexpr int W = DW < 32 ? DW : 32;
                 uint32_t o[W];
-                tmem_ld_n<W>(tmem + lane_bits + col_o + g * KP + c0, o);
+                tmem_ld_n<W>(tmem + lane_bits + col_o + ob * KP + (SPLIT ? g * DW : 0) + c0, o);
                 tmem_wait_ld();
                 if (!(p.diag & 4))
 #pragma unroll
@@ -776,7 +781,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&o_free[g]);
+            if (lane == 0) mbar_arrive(&o_free[ob]);
+        };
+        float* dsc_sm = xchg;  // [8][128]: per-row un-scale factors of the last 8 tiles (SPLIT mode)
+        int next_drain = 0;    // SPLIT mode: next tile this warpgroup has to drain
+        auto drain_through = [&](int last) {  // SPLIT mode: drain tiles next_drain .. last (inclusive)
+            for (; next_drain <= last; ++next_drain) {
+                const int t = next_drain;
+                mbar_wait(&o_full[t & 1], (uint32_t)((t >> 1) & 1));  // also orders the read of the owner's scale
+                drain(t & 1, (uint32_t)((t >> 1) & 1), dsc_sm[(t & 7) * TC_BM + row]);
+            }
         };
 
         // per-kernel constants of pass 1: z = S * za + (|y|^2 * zc + zx)
@@ -819,9 +833,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
+                if (SPLIT) dsc_sm[(u & 7) * TC_BM + row] = 1.0f;
+                __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[b]);
                 TC_PROF(4)
-                if (u >= 2) drain((uint32_t)(((u - 2) >> 1) & 1), 1.0f);
+                if (SPLIT) drain_through(u - 1);
+                else if (u >= 2) drain(g, (uint32_t)(((u - 2) >> 1) & 1), 1.0f);
                 TC_PROF(5)
             } else {
             // ---- pass 1: z_j and the row extreme ----
@@ -921,11 +938,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             TC_PROF(3)
             tmem_wait_st();
             tc_fence_before();
+            if (SPLIT) dsc_sm[(u & 7) * TC_BM + row] = dsc;  // published before p_full -> MMA2 -> o_full
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[b]);
             TC_PROF(4)
-            // drain this warpgroup's previous sub-tile while the tensor core works on this one
-            if (u >= 2) drain((uint32_t)(((u - 2) >> 1) & 1), dsc_prev);
+            // drain finished sub-tiles while the tensor core works on this one
+            if (SPLIT) drain_through(u - 1);
+            else if (u >= 2) drain(g, (uint32_t)(((u - 2) >> 1) & 1), dsc_prev);
             TC_PROF(5)
             dsc_prev = dsc;
             }
@@ -942,33 +961,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         }
         if (warp == 0) TC_PROF_FLUSH(8)
         else if (warp == 4) TC_PROF_FLUSH(16)
-        {
+        if (SPLIT) {
+            drain_through(T - 1);
+        } else {
             const int last = ((T - 1 - g) >> 1) * 2 + g;  // this warpgroup's last tile (T > g)
-            if (T > g) drain((uint32_t)((last >> 1) & 1), (p.diag & 2) ? 1.0f : dsc_prev);
+            if (T > g) drain(g, (uint32_t)((last >> 1) & 1), (p.diag & 2) ? 1.0f : dsc_prev);
         }
 
-        // ---- Y rows = warpgroup 0 partial + warpgroup 1 partial (through smem; all MMAs and loads are done) ----
-        float* ysm = reinterpret_cast<float*>(smem);  // [128][KP + 1], reuses the A ring
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // both warpgroups have drained their last tile
-        if (g == 1) {
+        if (SPLIT) {
+            // ---- each warpgroup holds complete sums for its half of the columns ----
+            if (grow < p.n) {
+                float* dst = p.out + (int64_t)blockIdx.z * p.split_stride + grow * p.ldo;
 #pragma unroll
-            for (int c = 0; c < KP / 2; ++c) {
-                float y0, y1;
-                unpack2(acc[c], y0, y1);
-                ysm[row * (KP + 1) + 2 * c] = y0;
-                ysm[row * (KP + 1) + 2 * c + 1] = y1;
+                for (int c = 0; c < DW / 2; ++c) {
+                    const int col = kc * KP + g * DW + 2 * c;
+                    float y0, y1;
+                    unpack2(acc[c], y0, y1);
+                    if (col < p.k) dst[col] = y0 * p.scale_out;
+                    if (col + 1 < p.k) dst[col + 1] = y1 * p.scale_out;
+                }
             }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (g == 0 && grow < p.n) {
-            float* dst = p.out + (int64_t)blockIdx.z * p.split_stride + grow * p.ldo;
+        } else {
+            // ---- Y rows = warpgroup 0 partial + warpgroup 1 partial (through smem; all MMAs and loads are done) ----
+            float* ysm = reinterpret_cast<float*>(smem);  // [128][KP + 1], reuses the A ring
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // both warpgroups have drained their last tile
+            if (g == 1) {
 #pragma unroll
-            for (int c = 0; c < KP / 2; ++c) {
-                const int col = kc * KP + 2 * c;
-                float y0, y1;
-                unpack2(acc[c], y0, y1);
-                if (col < p.k) dst[col] = (y0 + ysm[row * (KP + 1) + 2 * c]) * p.scale_out;
-                if (col + 1 < p.k) dst[col + 1] = (y1 + ysm[row * (KP + 1) + 2 * c + 1]) * p.scale_out;
+                for (int c = 0; c < DW / 2; ++c) {
+                    float y0, y1;
+                    unpack2(acc[c], y0, y1);
+                    ysm[row * (KP + 1) + 2 * c] = y0;
+                    ysm[row * (KP + 1) + 2 * c + 1] = y1;
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (g == 0 && grow < p.n) {
+                float* dst = p.out + (int64_t)blockIdx.z * p.split_stride + grow * p.ldo;
+#pragma unroll
+                for (int c = 0; c < DW / 2; ++c) {
+                    const int col = kc * KP + 2 * c;
+                    float y0, y1;
+                    unpack2(acc[c], y0, y1);
+                    if (col < p.k) dst[col] = (y0 + ysm[row * (KP + 1) + 2 * c]) * p.scale_out;
+                    if (col + 1 < p.k) dst[col + 1] = (y1 + ysm[row * (KP + 1) + 2 * c + 1]) * p.scale_out;
+                }
             }
         }
     }
@@ -995,6 +1031,9 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     const int kb = tc_kblocks(d);
     int kp = 16;
     while (kp < 64 && kp < k) kp *= 2;
+    // k > 64: 128-column chunks halve the number of times S and the pointwise stage are recomputed; they need
+    // 256 TMEM columns for the two O buffers, which leaves two S/P buffers for d <= 128
+    if (k > 64 && 64 * kb + 2 * 64 + 2 * 128 <= 512 && tc_env_int("RLAOPT_B200_TC_KP128", 1)) kp = 128;
     // TMEM columns: 64 KB (X hi/lo) + 64 NB (S/P) + 2 KP (O) <= 512
     int nb = (512 - 64 * kb - 2 * kp) / 64;
     if (nb > 4) nb = 4;
@@ -1004,7 +1043,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     la = max(1, min(nb >= 3 ? nb - 2 : 1, tc_env_int("RLAOPT_B200_TC_LA", la)));
     // smem: A ring (column-tile images) + V ring (la stages deeper: V of tile t is consumed la tiles after its A)
     const size_t a_stage = tc_image_bytes(kb), v_stage = tc_v_stage_bytes(kp);
-    const size_t fixed = 2 * 2 * TC_BM * sizeof(float) + 64 * sizeof(uint64_t) + 64;
+    const size_t fixed = 8 * TC_BM * sizeof(float) + 64 * sizeof(uint64_t) + 64;
     int sa = 4;
     while (sa > 2 && sa * a_stage + (sa + la) * v_stage + fixed > (size_t)TC_SMEM_LIMIT) --sa;
     int sv = sa + la;
@@ -1166,7 +1205,8 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     switch (pl.kp) {
         case 16: err = launch_tc_kp<16>(p, pl, n, stream); break;
         case 32: err = launch_tc_kp<32>(p, pl, n, stream); break;
-        default: err = launch_tc_kp<64>(p, pl, n, stream); break;
+        case 64: err = launch_tc_kp<64>(p, pl, n, stream); break;
+        default: err = launch_tc_kp<128>(p, pl, n, stream); break;
     }
     if (err != cudaSuccess) return err;
     if (pl.splits > 1) return launch_split_reduce<float>(part, pl.splits, n, k, Y, ldy, scale, stream);
