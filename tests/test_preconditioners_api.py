@@ -46,15 +46,15 @@ def test_nystrom(spd, precision, sketch, as_linop):
     assert P.U.dtype == precision and P.S.dtype == precision and P.U.device == DEVICE
     assert torch.all(P.S >= 0)
     assert torch.all(P.S[:-1] >= P.S[1:])  # descending, so S[-1] is the smallest (adaptive damping uses it)
-    assert torch.allclose(P.U.T @ P.U, torch.eye(20, dtype=precision), **tol)
-    x, X = torch.randn(50, dtype=precision), torch.randn(50, 5, dtype=precision)
+    assert torch.allclose(P.U.T @ P.U, torch.eye(20, dtype=precision, device=DEVICE), **tol)
+    x, X = torch.randn(50, dtype=precision, device=DEVICE), torch.randn(50, 5, dtype=precision, device=DEVICE)
     assert torch.allclose(P @ x, P.U @ (P.S * (P.U.T @ x)) + cfg.rho * x, **tol)
     assert torch.allclose(P @ X, P.U @ (P.S[:, None] * (P.U.T @ X)) + cfg.rho * X, **tol)
     for v in (x, X):
         inv = P._inv @ v
         assert inv.shape == v.shape and inv.dtype == precision
         assert torch.allclose(P @ inv, v, **tol)
-    explicit = P.U @ torch.diag(P.S) @ P.U.T + cfg.rho * torch.eye(50, dtype=precision)
+    explicit = P.U @ torch.diag(P.S) @ P.U.T + cfg.rho * torch.eye(50, dtype=precision, device=DEVICE)
     assert torch.allclose(explicit @ x, P @ x, **tol)
     # fixed damping ignores the baseline, adaptive adds the smallest Nystrom eigenvalue
     P._update_damping(2.0)
@@ -62,7 +62,7 @@ def test_nystrom(spd, precision, sketch, as_linop):
     Pa = Nystrom(NystromConfig(rank=20, sketch=sketch, rho=1e0, damping_mode="adaptive"))
     Pa._update(spd, DEVICE)
     Pa._update_damping(2.0)
-    assert torch.isclose(torch.as_tensor(Pa.config.rho, dtype=precision), 2.0 + Pa.S[-1])
+    assert torch.isclose(torch.as_tensor(Pa.config.rho, dtype=precision, device=DEVICE), 2.0 + Pa.S[-1])
     assert torch.allclose(Pa @ (Pa._inv @ x), x, **tol)
 
 
@@ -75,9 +75,9 @@ def test_newton(spd, precision, as_linop):
     P._update(_as_linop(spd) if as_linop else spd, DEVICE)
     assert torch.equal(spd, before)  # the caller's matrix is left alone (the reference adds rho in place)
     assert P.L.shape == (50, 50) and P.L.dtype == precision
-    M = spd + 1e-1 * torch.eye(50, dtype=precision)
+    M = spd + 1e-1 * torch.eye(50, dtype=precision, device=DEVICE)
     assert torch.allclose(P.L @ P.L.T, M, rtol=tol["rtol"], atol=tol["atol"] * float(M.abs().max()))
-    x, X = torch.randn(50, dtype=precision), torch.randn(50, 5, dtype=precision)
+    x, X = torch.randn(50, dtype=precision, device=DEVICE), torch.randn(50, 5, dtype=precision, device=DEVICE)
     scale = float(M.abs().max())
     assert torch.allclose(P @ x, M @ x, rtol=tol["rtol"], atol=tol["atol"] * scale)
     for v in (x, X):
@@ -141,15 +141,15 @@ def test_sketch_shapes_and_application(name, precision):
     S_left = get_sketch(name, "left", 8, 30, precision, DEVICE)
     assert S_right.Omega_mat.shape == (30, 8) and S_left.Omega_mat.shape == (8, 30)
     assert S_right.Omega_mat.is_contiguous() and S_right.Omega_mat.dtype == precision
-    M = torch.randn(30, 30, dtype=precision)
+    M = torch.randn(30, 30, dtype=precision, device=DEVICE)
     assert torch.allclose(S_right._apply_right(M), M @ S_right.Omega_mat)
     assert torch.allclose(S_right._apply_left_trans(M), S_right.Omega_mat.T @ M)
     assert torch.allclose(S_left._apply_left(M), S_left.Omega_mat @ M)
     assert torch.allclose(S_left._apply_right_trans(M), M @ S_left.Omega_mat.T)
     assert torch.allclose(S_right._apply_right(_as_linop(M + M.T)), (M + M.T) @ S_right.Omega_mat, **TOL[precision])
     if name == "ortho":
-        assert torch.allclose(S_right.Omega_mat.T @ S_right.Omega_mat, torch.eye(8, dtype=precision), **TOL[precision])
-        assert torch.allclose(S_left.Omega_mat @ S_left.Omega_mat.T, torch.eye(8, dtype=precision), **TOL[precision])
+        assert torch.allclose(S_right.Omega_mat.T @ S_right.Omega_mat, torch.eye(8, dtype=precision, device=DEVICE), **TOL[precision])
+        assert torch.allclose(S_left.Omega_mat @ S_left.Omega_mat.T, torch.eye(8, dtype=precision, device=DEVICE), **TOL[precision])
     with pytest.raises(ValueError):
         get_sketch("fourier", "right", 8, 30, precision, DEVICE)
     with pytest.raises(ValueError):
