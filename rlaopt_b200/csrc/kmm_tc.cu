@@ -33,8 +33,9 @@ namespace {
 
 constexpr int TC_BM = 128;      // rows per CTA (TMEM lanes)
 constexpr int TC_BN = 64;       // K columns per sub-tile
-constexpr int TC_EPI_WARPS = 8; // warps 0..7: pointwise; warp 8: producer; warp 9: MMA issue
-constexpr int TC_THREADS = (TC_EPI_WARPS + 4) * 32;  // warps 8..11: producer, MMA1 issue (even tiles), MMA2 issue, MMA1 issue (odd tiles)
+// NWG epilogue warpgroups (warps 0 .. 4 NWG - 1), then four control warps: producer, MMA1 issue (even tiles),
+// MMA2 issue, MMA1 issue (odd tiles)
+__host__ __device__ constexpr int tc_threads(int nwg) { return (nwg * 4 + 4) * 32; }
 constexpr int TC_MIN_SPLIT_TILES = 16;  // a column split covers at least 16 sub-tiles (1024 columns)
 constexpr int TC_KBLOCK_BYTES = 64 * 128;  // one K-block of a 64-row image: 64 rows x 128 B
 constexpr int TC_HEADER_BYTES = 256;
@@ -452,8 +453,10 @@ __host__ __device__ constexpr uint32_t tc_v_stage_bytes(int kp) { return (uint32
 //   [64 KB, +64 NB)              NB S/P buffers: S (64 fp32 columns) is overwritten in place by
 //                                P_hi (32 columns of fp16 pairs) | P_lo (32 columns)
 //   [64 KB + 64 NB, +2 KP)       two O buffers (one fresh accumulator per sub-tile, alternating)
-template <int KP>
-__global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p) {
+template <int KP, int NWG>
+__global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcParams p) {
+    constexpr int TC_EPI_WARPS = NWG * 4;
+    constexpr int NOB = NWG;  // O buffers: one per epilogue warpgroup (tile u accumulates into O[u % NWG])
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = p.kb, SA = p.a_stages, SV = p.v_stages, NB = p.nb;
@@ -472,9 +475,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
     uint64_t* s_full = v_empty + SV;     // [NB] MMA1 done
     uint64_t* p_full = s_full + NB;      // [NB] P written (8 warps)
     uint64_t* p_free = p_full + NB;      // [NB] MMA2 done reading P
-    uint64_t* o_full = p_free + NB;      // [2] O buffer complete
-    uint64_t* o_free = o_full + 2;       // [2] O buffer drained (8 warps)
-    uint64_t* x_full = o_free + 2;       // [1] X tile resident in TMEM (8 warps)
+    uint64_t* o_full = p_free + NB;      // [NOB] O buffer complete
+    uint64_t* o_free = o_full + NOB;     // [NOB] O buffer drained
+    uint64_t* x_full = o_free + NOB;     // [1] X tile resident in TMEM (8 warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 1);
 
     const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
@@ -495,14 +498,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         }
         for (int b = 0; b < NB; ++b) {
             mbar_init(&s_full[b], 1);
-            mbar_init(&p_full[b], TC_EPI_WARPS / 2);
+            mbar_init(&p_full[b], 4);  // the four warps of the owning warpgroup
             mbar_init(&p_free[b], 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NOB; ++b) {
             mbar_init(&o_full[b], 1);
-            mbar_init(&o_free[b], KP > 64 ? TC_EPI_WARPS : TC_EPI_WARPS / 2);
+            mbar_init(&o_free[b], KP > 64 ? 8 : 4);
         }
-        mbar_init(x_full, TC_EPI_WARPS);
+        mbar_init(x_full, 8);  // warpgroups 0 and 1 load the X tile
         fence_barrier_init();
     }
     if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, 512);
@@ -520,7 +523,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
 
     if (warp >= TC_EPI_WARPS) {
     // registers move from this warpgroup (producer, MMA issue, two idle warps) to the epilogue warpgroups
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if constexpr (NWG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == TC_EPI_WARPS) {
         // =============================== producer ===============================
         if (lane == 0) {
@@ -684,10 +688,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             uint32_t use2 = 0, phv = 0;
             TC_PROF_DECL
             for (int u = 0; u < T; ++u) {
-                const int ob = u & 1;
+                const int ob = u % NOB;
+                const uint32_t opar = (uint32_t)((u / NOB) & 1);  // use-count parity of O[ob]
                 TC_PROF(7)
                 // P written; V image landed; O[ob] of tile u - 2 has been drained
-                mbar_wait3(&p_full[b2], use2, &v_full[sv], phv, &o_free[ob], (uint32_t)(((u >> 1) & 1) ^ 1));
+                mbar_wait3(&p_full[b2], use2, &v_full[sv], phv, &o_free[ob], opar ^ 1);
                 TC_PROF(3)
                 tc_fence_after();
                 issue_mma2(b2, ob, sv);
@@ -712,7 +717,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         }
     }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        if constexpr (NWG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         // =============================== epilogue warps ===============================
         const int q = warp & 3;   // TMEM lane quarter this warp may access
         const int h = warp >> 2;  // column half of the sub-tile / of O handled by this warp
@@ -723,8 +729,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         const float nx = live ? reinterpret_cast<const float*>(p.rows + tc_norm_offset())[grow] : 0.0f;
         const float m2c = -2.0f * rh->inv_scale * ch->inv_scale;
 
-        // ---- X tile -> TMEM (h = 0: hi halves, h = 1: lo halves) ----
-        {
+        // ---- X tile -> TMEM (warpgroup 0: hi halves, warpgroup 1: lo halves) ----
+        if (h < 2) {
             const unsigned char* img = p.rows + tc_image_offset(p.n) + (size_t)(grow >> 6) * a_img_bytes +
                                        (size_t)h * KB * TC_KBLOCK_BYTES;
             const int r = (int)(grow & 63);
@@ -788,8 +794,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         auto drain_through = [&](int last) {  // SPLIT mode: drain tiles next_drain .. last (inclusive)
             for (; next_drain <= last; ++next_drain) {
                 const int t = next_drain;
-                mbar_wait(&o_full[t & 1], (uint32_t)((t >> 1) & 1));  // also orders the read of the owner's scale
-                drain(t & 1, (uint32_t)((t >> 1) & 1), dsc_sm[(t & 7) * TC_BM + row]);
+                mbar_wait(&o_full[t % NOB], (uint32_t)((t / NOB) & 1));  // also orders the read of the owner's scale
+                drain(t % NOB, (uint32_t)((t / NOB) & 1), dsc_sm[(t & 7) * TC_BM + row]);
             }
         };
 
@@ -803,11 +809,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         const bool is_rbf = p.kid == KID_RBF;
         const int kid = p.kid;
 
-        int b = g % NB, sv = g % SV;
+        int b = g % NB, sv = g % SV;  // NWG <= NB, SV
         uint32_t use = (uint32_t)((g / NB) & 1), phv = (uint32_t)((g / SV) & 1);
         float dsc_prev = 0.0f;
         TC_PROF_DECL
-        for (int u = g; u < T; u += 2) {
+        for (int u = g; u < T; u += NWG) {
             const unsigned char* vst = v_ring + (size_t)sv * v_stage_bytes;
             TC_PROF(7)
             // |y|^2 and the V scale of this sub-tile are in smem; MMA1 has written S[b]
@@ -838,7 +844,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
                 if (lane == 0) mbar_arrive(&p_full[b]);
                 TC_PROF(4)
                 if (SPLIT) drain_through(u - 1);
-                else if (u >= 2) drain(g, (uint32_t)(((u - 2) >> 1) & 1), 1.0f);
+                else if (u >= NWG) drain(g, (uint32_t)(((u - NWG) / NWG) & 1), 1.0f);
                 TC_PROF(5)
             } else {
             // ---- pass 1: z_j and the row extreme ----
@@ -944,16 +950,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
             TC_PROF(4)
             // drain finished sub-tiles while the tensor core works on this one
             if (SPLIT) drain_through(u - 1);
-            else if (u >= 2) drain(g, (uint32_t)(((u - 2) >> 1) & 1), dsc_prev);
+            else if (u >= NWG) drain(g, (uint32_t)(((u - NWG) / NWG) & 1), dsc_prev);
             TC_PROF(5)
             dsc_prev = dsc;
             }
-            b += 2;
+            b += NWG;
             if (b >= NB) {
                 b -= NB;
                 use ^= 1;
             }
-            sv += 2;
+            sv += NWG;
             if (sv >= SV) {
                 sv -= SV;
                 phv ^= 1;
@@ -964,8 +970,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
         if (SPLIT) {
             drain_through(T - 1);
         } else {
-            const int last = ((T - 1 - g) >> 1) * 2 + g;  // this warpgroup's last tile (T > g)
-            if (T > g) drain(g, (uint32_t)((last >> 1) & 1), (p.diag & 2) ? 1.0f : dsc_prev);
+            const int last = ((T - 1 - g) / NWG) * NWG + g;  // this warpgroup's last tile (T > g)
+            if (T > g) drain(g, (uint32_t)((last / NWG) & 1), (p.diag & 2) ? 1.0f : dsc_prev);
         }
 
         if (SPLIT) {
@@ -982,19 +988,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
                 }
             }
         } else {
-            // ---- Y rows = warpgroup 0 partial + warpgroup 1 partial (through smem; all MMAs and loads are done) ----
-            float* ysm = reinterpret_cast<float*>(smem);  // [128][KP + 1], reuses the A ring
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // both warpgroups have drained their last tile
-            if (g == 1) {
+            // ---- Y rows = sum of the warpgroups' partial rows (through smem; all MMAs and loads are done) ----
+            float* ysm = reinterpret_cast<float*>(smem);  // [NWG - 1][128][KP + 1], reuses the A ring
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");  // every warpgroup has drained its last tile
+            if (g >= 1) {
+                float* mine = ysm + (size_t)(g - 1) * TC_BM * (KP + 1);
 #pragma unroll
                 for (int c = 0; c < DW / 2; ++c) {
                     float y0, y1;
                     unpack2(acc[c], y0, y1);
-                    ysm[row * (KP + 1) + 2 * c] = y0;
-                    ysm[row * (KP + 1) + 2 * c + 1] = y1;
+                    mine[row * (KP + 1) + 2 * c] = y0;
+                    mine[row * (KP + 1) + 2 * c + 1] = y1;
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
             if (g == 0 && grow < p.n) {
                 float* dst = p.out + (int64_t)blockIdx.z * p.split_stride + grow * p.ldo;
 #pragma unroll
@@ -1002,8 +1009,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
                     const int col = kc * KP + 2 * c;
                     float y0, y1;
                     unpack2(acc[c], y0, y1);
-                    if (col < p.k) dst[col] = (y0 + ysm[row * (KP + 1) + 2 * c]) * p.scale_out;
-                    if (col + 1 < p.k) dst[col + 1] = (y1 + ysm[row * (KP + 1) + 2 * c + 1]) * p.scale_out;
+#pragma unroll
+                    for (int w = 0; w < NWG - 1; ++w) {
+                        y0 += ysm[(size_t)w * TC_BM * (KP + 1) + row * (KP + 1) + 2 * c];
+                        y1 += ysm[(size_t)w * TC_BM * (KP + 1) + row * (KP + 1) + 2 * c + 1];
+                    }
+                    if (col < p.k) dst[col] = y0 * p.scale_out;
+                    if (col + 1 < p.k) dst[col + 1] = y1 * p.scale_out;
                 }
             }
         }
@@ -1016,7 +1028,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) kmm_tc_kernel(const TcParams p)
 }
 
 struct TcPlan {
-    int kb, kp, k_chunks, a_stages, v_stages, nb, la, splits, tiles_per_split, pair;
+    int kb, kp, k_chunks, a_stages, v_stages, nb, la, nwg, splits, tiles_per_split, pair;
     int64_t sub_tiles;
     size_t smem_bytes, vimg_bytes, part_bytes;
 };
@@ -1034,11 +1046,15 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     // k > 64: 128-column chunks halve the number of times S and the pointwise stage are recomputed; they need
     // 256 TMEM columns for the two O buffers, which leaves two S/P buffers for d <= 128
     if (k > 64 && 64 * kb + 2 * 64 + 2 * 128 <= 512 && tc_env_int("RLAOPT_B200_TC_KP128", 1)) kp = 128;
-    // TMEM columns: 64 KB (X hi/lo) + 64 NB (S/P) + 2 KP (O) <= 512
-    int nb = (512 - 64 * kb - 2 * kp) / 64;
-    if (nb > 4) nb = 4;
+    // Small d and k: the tensor work per tile is small and the kernel is bound by the pointwise stage (MUFU, TMEM
+    // and mbarrier latencies); a third epilogue warpgroup keeps three tiles in flight per SM sub-partition.
+    int nwg = (kb <= 2 && kp <= 32 && tc_env_int("RLAOPT_B200_TC_NWG", 3) == 3) ? 3 : 2;
+    // TMEM columns: 64 KB (X hi/lo) + 64 NB (S/P) + NWG KP (O) <= 512
+    int nb = (512 - 64 * kb - nwg * kp) / 64;
+    if (nb > nwg + 2) nb = nwg + 2;
     if (nb < 2) return false;
-    nb = max(2, min(nb, tc_env_int("RLAOPT_B200_TC_NB", nb)));
+    if (nb < nwg) nwg = 2;
+    nb = max(nwg, min(nb, tc_env_int("RLAOPT_B200_TC_NB", nb)));
     int la = nb >= 4 ? 2 : 1;
     la = max(1, min(nb >= 3 ? nb - 2 : 1, tc_env_int("RLAOPT_B200_TC_LA", la)));
     // smem: A ring (column-tile images) + V ring (la stages deeper: V of tile t is consumed la tiles after its A)
@@ -1048,13 +1064,14 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     while (sa > 2 && sa * a_stage + (sa + la) * v_stage + fixed > (size_t)TC_SMEM_LIMIT) --sa;
     int sv = sa + la;
     if (sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) return false;
-    if (2 * sa + 2 * sv + 3 * nb + 5 > 64) return false;
+    if (2 * sa + 2 * sv + 3 * nb + 2 * 3 + 1 > 64) return false;
     pl->kb = kb;
     pl->kp = kp;
     pl->k_chunks = (int)((k + kp - 1) / kp);
     pl->a_stages = sa;
     pl->v_stages = sv;
     pl->nb = nb;
+    pl->nwg = nwg;
     pl->la = la;
     pl->sub_tiles = (m + TC_BN - 1) / TC_BN;
     // CTA pairs (clusters of two row blocks sharing every column-tile load through multicast): +3 % under the
@@ -1134,16 +1151,16 @@ size_t tc_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int sm_cou
     return round_up((int64_t)pl.vimg_bytes, 256) + pl.part_bytes;
 }
 
-template <int KP>
+template <int KP, int NWG>
 static cudaError_t launch_tc_kp(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
-    auto kern = kmm_tc_kernel<KP>;
+    auto kern = kmm_tc_kernel<KP, NWG>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (err != cudaSuccess) return err;
     unsigned row_blocks = (unsigned)((n + TC_BM - 1) / TC_BM);
     if (p.pair) row_blocks = (row_blocks + 1) & ~1u;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(row_blocks, (unsigned)pl.k_chunks, (unsigned)pl.splits);
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(tc_threads(NWG));
     cfg.dynamicSmemBytes = pl.smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -1203,10 +1220,10 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     }
     cudaError_t err;
     switch (pl.kp) {
-        case 16: err = launch_tc_kp<16>(p, pl, n, stream); break;
-        case 32: err = launch_tc_kp<32>(p, pl, n, stream); break;
-        case 64: err = launch_tc_kp<64>(p, pl, n, stream); break;
-        default: err = launch_tc_kp<128>(p, pl, n, stream); break;
+        case 16: err = pl.nwg == 3 ? launch_tc_kp<16, 3>(p, pl, n, stream) : launch_tc_kp<16, 2>(p, pl, n, stream); break;
+        case 32: err = pl.nwg == 3 ? launch_tc_kp<32, 3>(p, pl, n, stream) : launch_tc_kp<32, 2>(p, pl, n, stream); break;
+        case 64: err = launch_tc_kp<64, 2>(p, pl, n, stream); break;
+        default: err = launch_tc_kp<128, 2>(p, pl, n, stream); break;
     }
     if (err != cudaSuccess) return err;
     if (pl.splits > 1) return launch_split_reduce<float>(part, pl.splits, n, k, Y, ldy, scale, stream);
