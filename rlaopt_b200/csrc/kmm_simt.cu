@@ -202,8 +202,8 @@ kmm_simt_kernel(const T* __restrict__ Rt, int64_t n, int64_t n_pad,
         }
 
         // ---------------- phase 2: Yacc += P @ V ----------------
-#pragma unroll 4
-        for (int j = 0; j < BN; ++j) {
+#pragma unroll 32
+        for (int j = 0; j < BN; ++j) {  // unrolled by the swizzle period: (j >> 2) & 7 is a compile-time constant
             const int swz = (j >> 2) & 7;
             alignas(16) T p[RT];
             alignas(16) T v[CT];
