@@ -10,8 +10,18 @@ sequences ``V``, ``Y``) on the rows of the block only.
 The operator ``A_blk_oracle(blk)`` is built once per step and shared by the preconditioner and
 all power iterations (the reference rebuilds it for every matvec), and the
 block updates are scattered with ``index_add_`` instead of through dense zero matrices.
+
+Block sampling.  ``torch.multinomial`` over n uniform probabilities on the CPU costs O(n) per step
+(20 ms at n = 1M, 0.2 s at n = 10M -- more than the GPU work of the step).  Two measures:
+the next block is drawn by a helper thread while the GPU works on the current step (same CPU random
+stream, same blocks as the reference; disabled under ``host_rng`` where sketches share that stream),
+and ``SAP.block_sampler = "device"`` (or ``RLAOPT_B200_SAP_SAMPLER=device``) draws the block with
+``torch.multinomial`` on the GPU instead (different stream than the reference, no host work at all).
 """
 from __future__ import annotations
+
+import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -20,7 +30,7 @@ from rlaopt_b200.linops import LinOp
 from rlaopt_b200.preconditioners import (IdentityConfig, NewtonConfig, NystromConfig, Preconditioner,
                                          PreconditionerConfig, _get_precond)
 from rlaopt_b200.spectral_estimators import randomized_powering
-from rlaopt_b200.utils import sync_from_rank0
+from rlaopt_b200.utils import host_rng_enabled, sync_from_rank0
 
 from ._configs import SAPAccelConfig
 from ._solver import Solver
@@ -46,6 +56,10 @@ class SAP(Solver):
         n = system.A.shape[0]
         self.probs = torch.ones(n) / n  # host tensor: blocks are sampled on the CPU, as in the reference
         self.probs_cpu = self.probs.numpy()
+        self.block_sampler = os.environ.get("RLAOPT_B200_SAP_SAMPLER", "host")  # "host" (reference stream) | "device"
+        self._probs_dev = None
+        self._pool = None
+        self._next_blk = None
         if accel:
             mu, nu = accel_config.mu, accel_config.nu
             self.beta = 1 - (mu / nu) ** 0.5
@@ -59,14 +73,32 @@ class SAP(Solver):
         return self._W
 
     # ---- pieces of one step ----
-    def _get_blk(self) -> torch.Tensor:
+    def _draw_host_blk(self) -> torch.Tensor:
         try:
-            blk = torch.multinomial(self.probs, self.blk_sz, replacement=False)
+            return torch.multinomial(self.probs, self.blk_sz, replacement=False)
         except RuntimeError as err:  # more than 2^24 categories
             if "number of categories cannot exceed" not in str(err):
                 raise
             pick = np.random.choice(self.probs.shape[0], size=self.blk_sz, replace=False, p=self.probs_cpu)
-            blk = torch.from_numpy(pick)
+            return torch.from_numpy(pick)
+
+    def _get_blk(self) -> torch.Tensor:
+        if self.block_sampler == "device" and torch.device(self.device).type == "cuda":
+            if self._probs_dev is None:
+                self._probs_dev = self.probs.to(self.device)
+            if self._probs_dev.numel() < (1 << 24):
+                blk = torch.multinomial(self._probs_dev, self.blk_sz, replacement=False)
+            else:  # uniform sampling without replacement
+                blk = torch.randperm(self._probs_dev.numel(), device=self.device)[: self.blk_sz]
+            return sync_from_rank0(blk, self.device)
+        prefetch = torch.device(self.device).type == "cuda" and not host_rng_enabled()
+        if not prefetch:
+            blk = self._draw_host_blk()
+        else:  # the CPU stream is only consumed by these draws: drawing one step ahead keeps the sequence
+            if self._pool is None:
+                self._pool = ThreadPoolExecutor(max_workers=1)
+            blk = self._next_blk.result() if self._next_blk is not None else self._draw_host_blk()
+            self._next_blk = self._pool.submit(self._draw_host_blk)
         return sync_from_rank0(blk, self.device)  # SPMD runs: every rank works on rank 0's block
 
     def _get_precond(self, blk: torch.Tensor, A_bb=None) -> Preconditioner:

@@ -116,3 +116,45 @@ def test_krr_pcg_config1_shape():
     KW = ko.kernel_matmat(X, X, W.cpu().double(), "rbf", 1.0, row_idx=rows, dtype=torch.float64)
     res = B[rows].double() - (KW + 1.0 * W.cpu().double()[rows])
     assert torch.linalg.norm(res) <= 3e-4 * torch.linalg.norm(B[rows].double())
+
+
+def test_askotch_device_sampler_and_prefetch(monkeypatch):
+    """ASkotch with (a) host blocks prefetched by the helper thread -- the same block sequence as drawing them
+    synchronously -- and (b) blocks sampled on the GPU: unique indices, and the residual goes down."""
+    from rlaopt_b200.solvers import SAP
+    from rlaopt_b200.utils import host_rng
+
+    dev = torch.device("cuda:0")
+    case = load_cases("float32")["askotch_nystrom_gauss_rbf"]
+
+    def run(env, use_host_rng):
+        monkeypatch.setenv("RLAOPT_B200_SAP_SAMPLER", env)
+        blocks = []
+        orig = SAP._get_blk
+
+        def rec(self):
+            b = orig(self)
+            blocks.append(b.detach().cpu().clone())
+            return b
+
+        monkeypatch.setattr(SAP, "_get_blk", rec)
+        system = kernel_linsys(case, dev)
+        torch.manual_seed(11)
+        torch.cuda.manual_seed(11)
+        cfg = solver_config_for(case["name"], dev, 1e-4)
+        if use_host_rng:
+            with host_rng():
+                W, log = system.solve(cfg, torch.zeros(case["n"], case["k"], device=dev), callback_freq=20)
+        else:
+            W, log = system.solve(cfg, torch.zeros(case["n"], case["k"], device=dev), callback_freq=20)
+        monkeypatch.setattr(SAP, "_get_blk", orig)
+        rel = [float(log[i]["metrics"]["internal_metrics"]["rel_res"].max()) for i in sorted(log)]
+        return torch.stack(blocks), rel
+
+    sync_blocks, _ = run("host", True)       # synchronous draws (host_rng disables the prefetch)
+    pre_blocks, rel_pre = run("host", False)  # prefetched draws: same CPU stream, same sequence
+    assert torch.equal(sync_blocks, pre_blocks[: len(sync_blocks)])
+    dev_blocks, rel_dev = run("device", False)
+    assert all(len(torch.unique(b)) == len(b) for b in dev_blocks)
+    assert int(dev_blocks.min()) >= 0 and int(dev_blocks.max()) < case["n"]
+    assert rel_pre[-1] < 0.8 * rel_pre[0] and rel_dev[-1] < 0.8 * rel_dev[0]
