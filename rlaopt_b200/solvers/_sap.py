@@ -57,6 +57,7 @@ class SAP(Solver):
         self.probs = torch.ones(n) / n  # host tensor: blocks are sampled on the CPU, as in the reference
         self.probs_cpu = self.probs.numpy()
         self.block_sampler = os.environ.get("RLAOPT_B200_SAP_SAMPLER", "host")  # "host" (reference stream) | "device"
+        self.prefetch_blocks = os.environ.get("RLAOPT_B200_SAP_PREFETCH", "1") != "0"
         self._probs_dev = None
         self._pool = None
         self._next_blk = None
@@ -91,7 +92,7 @@ class SAP(Solver):
             else:  # uniform sampling without replacement
                 blk = torch.randperm(self._probs_dev.numel(), device=self.device)[: self.blk_sz]
             return sync_from_rank0(blk, self.device)
-        prefetch = torch.device(self.device).type == "cuda" and not host_rng_enabled()
+        prefetch = self.prefetch_blocks and torch.device(self.device).type == "cuda" and not host_rng_enabled()
         if not prefetch:
             blk = self._draw_host_blk()
         else:  # the CPU stream is only consumed by these draws: drawing one step ahead keeps the sequence

@@ -122,13 +122,13 @@ def test_askotch_device_sampler_and_prefetch(monkeypatch):
     """ASkotch with (a) host blocks prefetched by the helper thread -- the same block sequence as drawing them
     synchronously -- and (b) blocks sampled on the GPU: unique indices, and the residual goes down."""
     from rlaopt_b200.solvers import SAP
-    from rlaopt_b200.utils import host_rng
 
     dev = torch.device("cuda:0")
     case = load_cases("float32")["askotch_nystrom_gauss_rbf"]
 
-    def run(env, use_host_rng):
+    def run(env, prefetch):
         monkeypatch.setenv("RLAOPT_B200_SAP_SAMPLER", env)
+        monkeypatch.setenv("RLAOPT_B200_SAP_PREFETCH", "1" if prefetch else "0")
         blocks = []
         orig = SAP._get_blk
 
@@ -142,19 +142,15 @@ def test_askotch_device_sampler_and_prefetch(monkeypatch):
         torch.manual_seed(11)
         torch.cuda.manual_seed(11)
         cfg = solver_config_for(case["name"], dev, 1e-4)
-        if use_host_rng:
-            with host_rng():
-                W, log = system.solve(cfg, torch.zeros(case["n"], case["k"], device=dev), callback_freq=20)
-        else:
-            W, log = system.solve(cfg, torch.zeros(case["n"], case["k"], device=dev), callback_freq=20)
+        W, log = system.solve(cfg, torch.zeros(case["n"], case["k"], device=dev), callback_freq=20)
         monkeypatch.setattr(SAP, "_get_blk", orig)
         rel = [float(log[i]["metrics"]["internal_metrics"]["rel_res"].max()) for i in sorted(log)]
         return torch.stack(blocks), rel
 
-    sync_blocks, _ = run("host", True)       # synchronous draws (host_rng disables the prefetch)
-    pre_blocks, rel_pre = run("host", False)  # prefetched draws: same CPU stream, same sequence
+    sync_blocks, _ = run("host", False)      # synchronous draws, as the reference does
+    pre_blocks, rel_pre = run("host", True)  # prefetched draws: same CPU stream, same sequence
     assert torch.equal(sync_blocks, pre_blocks[: len(sync_blocks)])
-    dev_blocks, rel_dev = run("device", False)
+    dev_blocks, rel_dev = run("device", True)
     assert all(len(torch.unique(b)) == len(b) for b in dev_blocks)
     assert int(dev_blocks.min()) >= 0 and int(dev_blocks.max()) < case["n"]
     assert rel_pre[-1] < 0.8 * rel_pre[0] and rel_dev[-1] < 0.8 * rel_dev[0]
