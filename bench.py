@@ -43,6 +43,7 @@ WORKLOADS = {
     "c2": ("rbf", 1_000_000, 128, 64),
     "c3_laplace": ("laplace", 4_000_000, 32, 16),
     "c3_matern52": ("matern52", 4_000_000, 32, 16),
+    "c5_sketch": ("rbf", 2_000_000, 64, 1000),  # Nystrom sketch K @ Omega of BASELINE configs[4]
     "small": ("rbf", 65_536, 128, 64),
 }
 SM_COUNT_B200 = 148
