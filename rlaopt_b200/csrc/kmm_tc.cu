@@ -257,6 +257,37 @@ __device__ __forceinline__ float tc_value(float z) {
     else return fmaf(s, fmaf(s, 1.0f / 3.0f, 1.0f), 1.0f) * e;
 }
 
+// Exact squared distance of two packed points (direct differences of the fp16 hi + lo reconstructions), used by the
+// Matern-1/2 epilogue for (near-)coincident pairs, where the GEMM-form distance has no relative accuracy.
+// `xi` / `yj`: address of the point's row in K-block 0 of the hi image; `sw`: its swizzle key (index & 7).
+__device__ __noinline__ float tc_exact_dist2(const unsigned char* xi, int swx, const unsigned char* yj, int swy, int KB,
+                                             float inv_sx, float inv_sy) {
+    const size_t lo_off = (size_t)KB * (64 * 128);
+    float D = 0.0f;
+    for (int kb = 0; kb < KB; ++kb) {
+        for (int c = 0; c < 8; ++c) {
+            const size_t ox = (size_t)kb * (64 * 128) + (size_t)((c ^ swx) * 16);
+            const size_t oy = (size_t)kb * (64 * 128) + (size_t)((c ^ swy) * 16);
+            const uint4 xh = *reinterpret_cast<const uint4*>(xi + ox), xl = *reinterpret_cast<const uint4*>(xi + lo_off + ox);
+            const uint4 yh = *reinterpret_cast<const uint4*>(yj + oy), yl = *reinterpret_cast<const uint4*>(yj + lo_off + oy);
+            const __half2* xh2 = reinterpret_cast<const __half2*>(&xh);
+            const __half2* xl2 = reinterpret_cast<const __half2*>(&xl);
+            const __half2* yh2 = reinterpret_cast<const __half2*>(&yh);
+            const __half2* yl2 = reinterpret_cast<const __half2*>(&yl);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 a = __half22float2(xh2[e]), al = __half22float2(xl2[e]);
+                const float2 b = __half22float2(yh2[e]), bl = __half22float2(yl2[e]);
+                const float d0 = (a.x + al.x) * inv_sx - (b.x + bl.x) * inv_sy;
+                const float d1 = (a.y + al.y) * inv_sx - (b.y + bl.y) * inv_sy;
+                D = fmaf(d0, d0, D);
+                D = fmaf(d1, d1, D);
+            }
+        }
+    }
+    return D;
+}
+
 // ------------------------------------------------------------------------------------------
 // packing kernels
 // ------------------------------------------------------------------------------------------
@@ -453,7 +484,8 @@ __host__ __device__ constexpr uint32_t tc_v_stage_bytes(int kp) { return (uint32
 //   [64 KB, +64 NB)              NB S/P buffers: S (64 fp32 columns) is overwritten in place by
 //                                P_hi (32 columns of fp16 pairs) | P_lo (32 columns)
 //   [64 KB + 64 NB, +2 KP)       two O buffers (one fresh accumulator per sub-tile, alternating)
-template <int KP, int NWG>
+// M12: instantiation for Matern-1/2 (carries the near-point recompute; the other kernels stay free of its code)
+template <int KP, int NWG, bool M12>
 __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcParams p) {
     constexpr int TC_EPI_WARPS = NWG * 4;
     constexpr int NOB = NWG;  // O buffers: one per epilogue warpgroup (tile u accumulates into O[u % NWG])
@@ -880,6 +912,36 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                     unpack2(z[i], z0, z1);
                     ext = min3(ext, z0, z1);
                 }
+                // Matern-1/2 is not smooth at r = 0: exp(-sqrt(D)) turns the absolute error eps (|x|^2 + |y|^2) of the
+                // GEMM-form D into eps (|x|^2 + |y|^2) / (2 r).  Pairs with D < 2.25e-4 (|x|^2 + |y|^2)^2 (error above
+                // ~1e-5) are recomputed from direct differences of the packed points; rows without such a pair
+                // (the usual case: only the diagonal of K(X, X) has them) pay one compare per tile.
+                if constexpr (M12) if (live && ext < 1.0e-3f * nx * nx) {
+                    const int64_t j0 = (t_begin + u) * TC_BN;
+                    const unsigned char* xi = p.rows + tc_image_offset(p.n) + (size_t)(grow >> 6) * a_img_bytes +
+                                              (size_t)(grow & 63) * 128;
+                    const float* nyf = reinterpret_cast<const float*>(vst + v_norm_off);
+                    // slow path: z goes through a thread-local array so that the scan can use a run-time index
+                    // (the unrolled copies keep z itself in registers on the fast path)
+                    float zl[TC_BN];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) unpack2(z[i], zl[2 * i], zl[2 * i + 1]);
+#pragma unroll 1
+                    for (int j = 0; j < TC_BN; ++j) {
+                        const float s2 = nx + nyf[j];
+                        if (zl[j] < 2.25e-4f * s2 * s2 && j0 + j < p.m) {
+                            const int64_t jg = j0 + j;
+                            const unsigned char* yj = col_images + (size_t)(jg >> 6) * a_img_bytes + (size_t)(jg & 63) * 128;
+                            zl[j] = tc_exact_dist2(xi, (int)(grow & 7), yj, (int)(jg & 7), KB, rh->inv_scale, ch->inv_scale);
+                        }
+                    }
+                    ext = 3.0e38f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        z[i] = pack2(zl[2 * i], zl[2 * i + 1]);
+                        ext = min3(ext, zl[2 * i], zl[2 * i + 1]);
+                    }
+                }
             }
             // P' = P * 2^E with max_j P' in [2^14, 2^15): the fp16 hi/lo pair keeps 22 bits of the row's large entries
             int E;
@@ -1151,9 +1213,9 @@ size_t tc_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int sm_cou
     return round_up((int64_t)pl.vimg_bytes, 256) + pl.part_bytes;
 }
 
-template <int KP, int NWG>
-static cudaError_t launch_tc_kp(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
-    auto kern = kmm_tc_kernel<KP, NWG>;
+template <int KP, int NWG, bool M12>
+static cudaError_t launch_tc_inst(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
+    auto kern = kmm_tc_kernel<KP, NWG, M12>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (err != cudaSuccess) return err;
     unsigned row_blocks = (unsigned)((n + TC_BM - 1) / TC_BM);
@@ -1171,6 +1233,12 @@ static cudaError_t launch_tc_kp(const TcParams& p, const TcPlan& pl, int64_t n, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <int KP, int NWG>
+static cudaError_t launch_tc_kp(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
+    return p.kid == KID_MATERN12 ? launch_tc_inst<KP, NWG, true>(p, pl, n, stream)
+                                 : launch_tc_inst<KP, NWG, false>(p, pl, n, stream);
 }
 
 cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packed, int64_t m, int64_t d,

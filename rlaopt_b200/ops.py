@@ -73,11 +73,8 @@ def choose_layout(kid: int, dtype: torch.dtype, d: int, k: int) -> int:
         return LAYOUT_SIMT
     elem = 4 if dtype == torch.float32 else 8
     tc_ok = bool(_lib.load().rlaopt_b200_layout_supported(kid, elem, d, k, LAYOUT_TC))
-    if kid == KERNEL_IDS["matern12"] and forced != "tc":
-        # exp(-r) is not smooth at r = 0: the GEMM-form distance |x|^2+|y|^2-2x.y leaves an
-        # O(sqrt(eps)) error on (near-)coincident points, so Matern-1/2 stays on the
-        # direct-difference CUDA-core kernel (SURVEY §7 "hard parts").
-        tc_ok = False
+    # Matern-1/2 (exp(-r), not smooth at r = 0) also runs on the tensor-core path: its epilogue recomputes
+    # (near-)coincident pairs from direct differences, where the GEMM-form distance has no relative accuracy.
     if forced == "tc":
         if not tc_ok:
             raise RuntimeError(f"RLAOPT_B200_LAYOUT=tc but kernel={_KERNEL_NAMES[kid]} dtype={dtype} d={d} k={k} unsupported")

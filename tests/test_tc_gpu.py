@@ -11,7 +11,7 @@ from oracle import kernel_oracle as ko
 
 pytestmark = pytest.mark.gpu
 
-TC_KERNELS = ["rbf", "matern32", "matern52"]
+TC_KERNELS = ["rbf", "matern12", "matern32", "matern52"]
 
 
 def _rand(shape, seed):
@@ -34,10 +34,10 @@ def test_layout_selection(dev):
     assert ops.choose_layout(ops.KERNEL_IDS["rbf"], f32, 500, 10) == LAYOUT_SIMT  # d > 192
     assert ops.choose_layout(ops.KERNEL_IDS["rbf"], f64, 128, 64) == LAYOUT_SIMT  # fp64
     assert ops.choose_layout(ops.KERNEL_IDS["laplace"], f32, 32, 16) == LAYOUT_SIMT  # L1 distance
-    assert ops.choose_layout(ops.KERNEL_IDS["matern12"], f32, 32, 16) == LAYOUT_SIMT  # non-smooth at r = 0
+    assert ops.choose_layout(ops.KERNEL_IDS["matern12"], f32, 32, 16) == LAYOUT_TC  # near pairs recomputed exactly
 
 
-@pytest.mark.parametrize("name", TC_KERNELS + ["matern12"])
+@pytest.mark.parametrize("name", TC_KERNELS)
 @pytest.mark.parametrize(
     "n,m,d,k",
     [(1, 1, 1, 1), (2, 3, 3, 2), (127, 129, 33, 17), (129, 300, 16, 64), (300, 257, 128, 70), (200, 1000, 192, 130),
@@ -52,7 +52,6 @@ def test_tc_against_fp64_oracle(dev, name, n, m, d, k):
     ref = ko.kernel_matmat_gemm_form(A1, A2, V, name, 0.9, 1.7, dtype=torch.float64)
     got = kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), name, 0.9, 1.7, layout=LAYOUT_TC)
     assert got.shape == (n, k)
-    # Matern-1/2 is only offered on this path on request; away from r = 0 it meets the same bar
     assert ko.rel_fro_error(got, ref) <= 1e-5, (name, n, m, d, k)
     ref_t = ko.kernel_matmat_gemm_form(A2, A1, W, name, 0.9, 1.7, dtype=torch.float64)
     got_t = kernel_matmat(A1.to(dev), A2.to(dev), W.to(dev), name, 0.9, 1.7, transpose=True, layout=LAYOUT_TC)
@@ -195,3 +194,40 @@ def test_k_chunks_and_wide_features(dev):
         ref = ko.kernel_matmat_gemm_form(A1, A2, V, "matern32", 1.3, dtype=torch.float64)
         got = kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), "matern32", 1.3, layout=LAYOUT_TC)
         assert ko.rel_fro_error(got, ref) <= 1e-5, (n, m, d, k)
+
+
+@pytest.mark.parametrize("d,ls", [(3, 0.02), (16, 0.05), (128, 0.2), (40, 1.0)])
+def test_matern12_coincident_and_near_points(dev, d, ls):
+    """exp(-r) amplifies the GEMM-form distance error near r = 0 (error eps (|x|^2 + |y|^2) / 2r): the diagonal of
+    K(X, X), exact duplicates across operands and near-duplicates are recomputed from direct differences.
+    Small lengthscales make K ~ I + (few near neighbours), the regime where those entries dominate Y."""
+    from rlaopt_b200._lib import LAYOUT_SIMT, LAYOUT_TC
+    from rlaopt_b200.ops import kernel_matmat
+
+    n, k = 1500, 5
+    X = _rand((n, d), 31) / d**0.5
+    X[100:200] = X[:100]                                   # exact duplicates
+    X[200:300] = X[:100] + 1e-5 * _rand((100, d), 32)      # near duplicates
+    X[300:400] = X[:100] + 3e-3 * _rand((100, d), 33)      # close points
+    V = _rand((n, k), 34)
+    ref = ko.kernel_matmat(X, X, V, "matern12", ls, dtype=torch.float64)  # direct differences in fp64
+    got = kernel_matmat(X.to(dev), X.to(dev), V.to(dev), "matern12", ls, layout=LAYOUT_TC)
+    simt = kernel_matmat(X.to(dev), X.to(dev), V.to(dev), "matern12", ls, layout=LAYOUT_SIMT)
+    assert ko.rel_fro_error(got, ref) <= 1e-5, (d, ls, ko.rel_fro_error(got, ref), ko.rel_fro_error(simt, ref))
+    # different operands holding the same points (separate packs, separate scales)
+    A2 = torch.cat([X[:700] * 1.0, _rand((300, d), 35) / d**0.5 * 3.0])
+    W = _rand((A2.shape[0], k), 36)
+    ref2 = ko.kernel_matmat(X, A2, W, "matern12", ls, dtype=torch.float64)
+    got2 = kernel_matmat(X.to(dev), A2.to(dev), W.to(dev), "matern12", ls, layout=LAYOUT_TC)
+    assert ko.rel_fro_error(got2, ref2) <= 1e-5
+
+
+def test_matern12_diagonal_is_exact(dev):
+    from rlaopt_b200._lib import LAYOUT_TC
+    from rlaopt_b200.ops import kernel_matmat
+
+    n, d = 640, 24
+    X = (_rand((n, d), 37) * 5.0).to(dev)  # |x|^2 ~ 600: far points, K = I to fp32 precision
+    Y = kernel_matmat(X, X, torch.eye(n, device=dev), "matern12", 0.05, layout=LAYOUT_TC)
+    assert torch.equal(Y.diagonal(), torch.ones(n, device=dev))
+    assert float((Y - torch.eye(n, device=dev)).abs().max()) <= 1e-6
