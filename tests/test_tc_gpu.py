@@ -41,7 +41,8 @@ def test_layout_selection(dev):
 @pytest.mark.parametrize(
     "n,m,d,k",
     [(1, 1, 1, 1), (2, 3, 3, 2), (127, 129, 33, 17), (129, 300, 16, 64), (300, 257, 128, 70), (200, 1000, 192, 130),
-     (1000, 77, 50, 16), (64, 20000, 8, 1), (5000, 5000, 128, 64)],
+     (1000, 77, 50, 16), (64, 20000, 8, 1), (5000, 5000, 128, 64), (700, 900, 128, 16), (300, 2000, 100, 1),
+     (513, 1000, 64, 32), (40000, 300, 16, 2)],
 )
 def test_tc_against_fp64_oracle(dev, name, n, m, d, k):
     from rlaopt_b200._lib import LAYOUT_TC
