@@ -1161,8 +1161,9 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
         // ~20x the algorithmic bytes at C2 (+3 % under the power cap) for splits x n x k floats of workspace.
         const size_t tile_bytes = tc_image_bytes(kb) + (size_t)kp * 256;
         int64_t cap = tc_env_int("RLAOPT_B200_TC_SPLIT_TILES", -1);
+        const bool forced = cap > 0;  // tests force small chunks on small problems
         if (cap < 0) cap = (int64_t)((48u << 20) / tile_bytes);
-        if (cap > 0 && base >= target && (size_t)pl->sub_tiles * tile_bytes > ((size_t)64 << 20)) {
+        if (cap > 0 && (forced || (base >= target && (size_t)pl->sub_tiles * tile_bytes > ((size_t)64 << 20)))) {
             if (cap < TC_MIN_SPLIT_TILES) cap = TC_MIN_SPLIT_TILES;
             const int64_t floor_tps = (pl->sub_tiles + 31) / 32;  // at most 32 partial buffers
             if (cap < floor_tps) cap = floor_tps;
