@@ -16,6 +16,13 @@ from rlaopt_b200.preconditioners import PreconditionerConfig, _get_precond
 from ._solver import Solver
 
 
+def _small_solve(G: torch.Tensor, rhs: torch.Tensor) -> torch.Tensor:
+    """``G^{-1} rhs`` for the k x k Gram systems; a single right-hand side is a division (no LU, no host sync)."""
+    if G.shape[0] == 1:
+        return rhs / G
+    return torch.linalg.solve(G, rhs)
+
+
 class PCG(Solver):
     def __init__(self, system, W_init: torch.Tensor, precond_config: PreconditionerConfig, device: torch.device):
         self.system = system
@@ -56,12 +63,12 @@ class PCG(Solver):
     def _step_all(self):
         D = self.P_
         AD = self._apply(D)
-        alpha = torch.linalg.solve(D.T @ AD, self.RZ)
+        alpha = _small_solve(D.T @ AD, self.RZ)
         self._W.addmm_(D, alpha)
         self.R.addmm_(AD, alpha, alpha=-1.0)
         self.Z = self.P._inv @ self.R
         RZ_new = self.R.T @ self.Z
-        beta = torch.linalg.solve(self.RZ, RZ_new)
+        beta = _small_solve(self.RZ, RZ_new)
         self.P_ = torch.addmm(self.Z, D, beta)
         self.RZ = RZ_new
 
@@ -70,14 +77,14 @@ class PCG(Solver):
         D = self.P_[:, idx]
         RZ = self.RZ[idx][:, idx]
         AD = self._apply(D)
-        alpha = torch.linalg.solve(D.T @ AD, RZ)
+        alpha = _small_solve(D.T @ AD, RZ)
         self._W[:, idx] += D @ alpha
         R_act = self.R[:, idx] - AD @ alpha
         self.R[:, idx] = R_act
         Z_act = self.P._inv @ R_act
         self.Z[:, idx] = Z_act
         RZ_new = R_act.T @ Z_act
-        beta = torch.linalg.solve(RZ, RZ_new)
+        beta = _small_solve(RZ, RZ_new)
         self.P_[:, idx] = Z_act + D @ beta
         full = torch.zeros_like(self.RZ)
         full[idx.unsqueeze(1), idx.unsqueeze(0)] = RZ_new
