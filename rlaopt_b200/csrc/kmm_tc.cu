@@ -39,7 +39,9 @@ __host__ __device__ constexpr int tc_threads(int nwg) { return (nwg * 4 + 4) * 3
 constexpr int TC_MIN_SPLIT_TILES = 16;  // a column split covers at least 16 sub-tiles (1024 columns)
 constexpr int TC_KBLOCK_BYTES = 64 * 128;  // one K-block of a 64-row image: 64 rows x 128 B
 constexpr int TC_HEADER_BYTES = 256;
-constexpr int TC_MAX_D = 192;
+constexpr int TC_MAX_D = 192;        // X tile resident in TMEM up to here
+constexpr int TC_MAX_D_WIDE = 2048;  // beyond: X and Y stream through smem one 64-feature K-block at a time
+constexpr uint32_t TC_WIDE_STAGE_BYTES = 8 * TC_KBLOCK_BYTES;  // {X hi, X lo, Y hi, Y lo} x 128 rows x 128 B
 constexpr int TC_SMEM_LIMIT = 220 * 1024;
 
 struct TcHeader {
@@ -431,6 +433,7 @@ struct TcParams {
     int k, kb, nk1, kid;
     int a_stages, v_stages;  // smem ring depths (column-tile images / V images + norms)
     int nb, la;              // S/P buffers in TMEM, MMA1 look-ahead (tiles)
+    int wide;                // 1: d > 192, feature-chunked MMA1 with X and Y K-blocks streamed through the A ring
     int pair;                // 1: launched as clusters of two CTAs that share every column-tile load (multicast halves)
     int diag;                // RLAOPT_B200_TC_DIAG knock-outs (profiling only): 1 no MMA, 2 no pointwise, 4 no drain, 8 no loads
     float scale_out;
@@ -475,6 +478,22 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
     else tmem_ld8(taddr, r);
 }
 
+// tcgen05.mma kind::f16 with both operands in shared memory (wide-d variant)
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t desc_hi,
+                                        uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 ad, bd;\n"
+        "mov.b64 ad, {%1, %3};\n"
+        "mov.b64 bd, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(adesc_lo), "r"(bdesc_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
 // shared-memory footprint of one V-ring stage: image (hi | lo), 16 B trailer, 64 column norms; 1 KB aligned
 __host__ __device__ constexpr uint32_t tc_v_stage_bytes(int kp) { return (uint32_t)kp * 256 + 1024; }
 
@@ -492,12 +511,13 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = p.kb, SA = p.a_stages, SV = p.v_stages, NB = p.nb;
-    const uint32_t a_img_bytes = (uint32_t)tc_image_bytes(KB);  // hi + lo
+    const uint32_t a_img_bytes = (uint32_t)tc_image_bytes(KB);  // hi + lo image of one 64-point tile in HBM
+    const uint32_t a_stage_bytes = p.wide ? TC_WIDE_STAGE_BYTES : a_img_bytes;  // one slot of the A ring
     constexpr uint32_t v_img_bytes = KP * 256 + 16;             // hi + lo + trailer, as stored in HBM
     constexpr uint32_t v_stage_bytes = tc_v_stage_bytes(KP);
     constexpr uint32_t v_norm_off = KP * 256 + 16;
     unsigned char* a_ring = smem;
-    unsigned char* v_ring = smem + (size_t)SA * a_img_bytes;
+    unsigned char* v_ring = smem + (size_t)SA * a_stage_bytes;
     float* xchg = reinterpret_cast<float*>(v_ring + (size_t)SV * v_stage_bytes);  // [2][2][128] row-max exchange
     uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 8 * TC_BM);
     uint64_t* a_full = bars;             // [SA] producer -> MMA1
@@ -546,7 +566,8 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     if (p.pair) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t col_a_hi = 0, col_a_lo = KB * 32, col_sp = KB * 64, col_o = KB * 64 + NB * 64;
+    const uint32_t x_cols = p.wide ? 0 : KB * 64;  // wide-d: X is not resident in TMEM
+    const uint32_t col_a_hi = 0, col_a_lo = KB * 32, col_sp = x_cols, col_o = x_cols + NB * 64;
 
     const TcHeader* rh = reinterpret_cast<const TcHeader*>(p.rows);
     const TcHeader* ch = reinterpret_cast<const TcHeader*>(p.cols);
@@ -566,6 +587,51 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             int sa = 0, sv = 0;
             uint32_t pha = 1, phv = 1;  // a fresh barrier passes a wait on parity 1
             const uint32_t crank = p.pair ? cluster_ctarank() : 0;
+            if (p.wide) {
+                // Wide d: per segment of two column tiles, first their V images, then one A-ring slot per 64-feature
+                // K-block: {X hi, X lo} of this CTA's 128 rows and {Y hi, Y lo} of the segment's 128 columns.
+                const bool rows_live = row0 < tc_npad(p.n);
+                const unsigned char* x_img = p.rows + tc_image_offset(p.n) + (size_t)(row0 >> 6) * a_img_bytes;
+                const size_t lo_img = (size_t)KB * TC_KBLOCK_BYTES;
+                for (int u0 = 0; u0 < T; u0 += 2) {
+                    const int cnt = (u0 + 1 < T) ? 2 : 1;
+                    for (int e = 0; e < cnt; ++e) {
+                        mbar_wait(&v_empty[sv], phv);
+                        unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
+                        mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
+                        bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
+                        bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
+                        v_src += v_img_bytes;
+                        n_src += TC_BN;
+                        if (++sv == SV) {
+                            sv = 0;
+                            phv ^= 1;
+                        }
+                    }
+                    for (int kb = 0; kb < KB; ++kb) {
+                        mbar_wait(&a_empty[sa], pha);
+                        unsigned char* dst = a_ring + (size_t)sa * a_stage_bytes;
+                        mbar_arrive_expect_tx(&a_full[sa], (rows_live ? 4u : 0u) * TC_KBLOCK_BYTES + 2u * cnt * TC_KBLOCK_BYTES);
+                        const size_t koff = (size_t)kb * TC_KBLOCK_BYTES;
+                        if (rows_live) {
+                            bulk_copy_g2s(dst, x_img + koff, TC_KBLOCK_BYTES, &a_full[sa]);
+                            bulk_copy_g2s(dst + TC_KBLOCK_BYTES, x_img + a_img_bytes + koff, TC_KBLOCK_BYTES, &a_full[sa]);
+                            bulk_copy_g2s(dst + 2 * TC_KBLOCK_BYTES, x_img + lo_img + koff, TC_KBLOCK_BYTES, &a_full[sa]);
+                            bulk_copy_g2s(dst + 3 * TC_KBLOCK_BYTES, x_img + a_img_bytes + lo_img + koff, TC_KBLOCK_BYTES, &a_full[sa]);
+                        }
+                        for (int e = 0; e < cnt; ++e) {
+                            const unsigned char* y_img = a_src + (size_t)e * a_img_bytes + koff;
+                            bulk_copy_g2s(dst + (4 + e) * TC_KBLOCK_BYTES, y_img, TC_KBLOCK_BYTES, &a_full[sa]);
+                            bulk_copy_g2s(dst + (6 + e) * TC_KBLOCK_BYTES, y_img + lo_img, TC_KBLOCK_BYTES, &a_full[sa]);
+                        }
+                        if (++sa == SA) {
+                            sa = 0;
+                            pha ^= 1;
+                        }
+                    }
+                    a_src += (size_t)cnt * a_img_bytes;
+                }
+            } else
             for (int u = 0; u < T; ++u) {
                 mbar_wait(&a_empty[sa], pha);
                 if (p.diag & 8) {
@@ -684,6 +750,51 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             // MMA2 as far as the NB S/P buffers and the A ring allow; while one of them polls its barriers the
             // other's instructions keep the tensor pipe fed ----
             const int par = (warp == TC_EPI_WARPS + 1) ? 0 : 1;
+            if (p.wide) {
+                // Wide d (warp 9 only): S[b0], S[b0 + 1] of a two-tile segment accumulate over the K-blocks with
+                // M128 x N128 x K16 MMAs, both operands from the A-ring slot (SS mode runs at the full rate for N = 128)
+                if (par == 0) {
+                    constexpr uint32_t idesc_w = umma_idesc(FMT_F16, 2 * TC_BN);
+                    int sa = 0;
+                    uint32_t pha = 0;
+                    for (int u0 = 0; u0 < T; u0 += 2) {
+                        const int b0 = u0 % NB;                        // NB = 4: segments alternate between buffers {0,1} and {2,3}
+                        const uint32_t use = (uint32_t)((u0 / NB) & 1);
+                        mbar_wait2(&p_free[b0], use ^ 1, &p_free[b0 + 1], use ^ 1);  // MMA2 of the segment NB tiles back
+                        const uint32_t d_t = tmem + col_sp + b0 * 64;
+                        for (int kb = 0; kb < KB; ++kb) {
+                            mbar_wait(&a_full[sa], pha);
+                            tc_fence_after();
+                            const uint32_t st = a_ring_base + (uint32_t)sa * a_stage_bytes;
+                            const uint32_t xh = desc_lo0 + (st >> 4), xl = desc_lo0 + ((st + 2 * TC_KBLOCK_BYTES) >> 4);
+                            const uint32_t yh = desc_lo0 + ((st + 4 * TC_KBLOCK_BYTES) >> 4);
+                            const uint32_t yl = desc_lo0 + ((st + 6 * TC_KBLOCK_BYTES) >> 4);
+                            const int steps = min(4, nk1 - 4 * kb);
+                            if (!(p.diag & 1) && elect_one()) {
+#pragma unroll 1
+                                for (int part = 0; part < 3; ++part) {
+                                    const uint32_t ad = (part == 1 ? xl : xh), bd = (part == 0 ? yl : yh);
+#pragma unroll 1
+                                    for (int ks = 0; ks < steps; ++ks)
+                                        umma_ss(d_t, ad + 2 * ks, bd + 2 * ks, desc_hi, idesc_w, (uint32_t)((kb | part | ks) != 0));
+                                }
+                            }
+                            __syncwarp();
+                            if (elect_one()) umma_commit(&a_empty[sa]);
+                            __syncwarp();
+                            if (++sa == SA) {
+                                sa = 0;
+                                pha ^= 1;
+                            }
+                        }
+                        if (elect_one()) {
+                            umma_commit(&s_full[b0]);
+                            umma_commit(&s_full[b0 + 1]);
+                        }
+                        __syncwarp();
+                    }
+                }
+            } else {
             mbar_wait(x_full, 0);
             int b1 = par % NB, sa = par % SA;
             uint32_t use1 = (uint32_t)((par / NB) & 1), pha = (uint32_t)((par / SA) & 1);
@@ -714,6 +825,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                 }
             }
             if (par == 0) TC_PROF_FLUSH(0)
+            }
         } else {
             // ---- MMA2 issuer ----
             int b2 = 0, sv = 0;
@@ -762,7 +874,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         const float m2c = -2.0f * rh->inv_scale * ch->inv_scale;
 
         // ---- X tile -> TMEM (warpgroup 0: hi halves, warpgroup 1: lo halves) ----
-        if (h < 2) {
+        if (h < 2 && !p.wide) {
             const unsigned char* img = p.rows + tc_image_offset(p.n) + (size_t)(grow >> 6) * a_img_bytes +
                                        (size_t)h * KB * TC_KBLOCK_BYTES;
             const int r = (int)(grow & 63);
@@ -1090,7 +1202,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
 }
 
 struct TcPlan {
-    int kb, kp, k_chunks, a_stages, v_stages, nb, la, nwg, splits, tiles_per_split, pair;
+    int kb, kp, k_chunks, a_stages, v_stages, nb, la, nwg, wide, splits, tiles_per_split, pair;
     int64_t sub_tiles;
     size_t smem_bytes, vimg_bytes, part_bytes;
 };
@@ -1101,30 +1213,39 @@ int tc_env_int(const char* name, int dflt) {
 }
 
 bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* pl) {
-    if (d < 1 || d > TC_MAX_D || n < 1 || m < 1 || k < 1) return false;
+    if (d < 1 || d > TC_MAX_D_WIDE || n < 1 || m < 1 || k < 1) return false;
+    const bool wide = d > TC_MAX_D;
     const int kb = tc_kblocks(d);
     int kp = 16;
     while (kp < 64 && kp < k) kp *= 2;
     // k > 64: 128-column chunks halve the number of times S and the pointwise stage are recomputed; they need
     // 256 TMEM columns for the two O buffers, which leaves two S/P buffers for d <= 128
-    if (k > 64 && 64 * kb + 2 * 64 + 2 * 128 <= 512 && tc_env_int("RLAOPT_B200_TC_KP128", 1)) kp = 128;
+    if (!wide && k > 64 && 64 * kb + 2 * 64 + 2 * 128 <= 512 && tc_env_int("RLAOPT_B200_TC_KP128", 1)) kp = 128;
     // Small d and k: the tensor work per tile is small and the kernel is bound by the pointwise stage (MUFU, TMEM
     // and mbarrier latencies); a third epilogue warpgroup keeps three tiles in flight per SM sub-partition.
     int nwg = (kb <= 2 && kp <= 32 && tc_env_int("RLAOPT_B200_TC_NWG", 3) == 3) ? 3 : 2;
+    const int x_cols = wide ? 0 : 64 * kb;  // wide d: X streams through smem, only S/P and O live in TMEM
     // TMEM columns: 64 KB (X hi/lo) + 64 NB (S/P) + NWG KP (O) <= 512
-    int nb = (512 - 64 * kb - nwg * kp) / 64;
+    int nb = (512 - x_cols - nwg * kp) / 64;
     if (nb > nwg + 2) nb = nwg + 2;
     if (nb < 2) return false;
     if (nb < nwg) nwg = 2;
-    nb = max(nwg, min(nb, tc_env_int("RLAOPT_B200_TC_NB", nb)));
+    if (wide) nb = 4, nwg = 2;  // two-tile segments, double buffered
+    if (!wide) nb = max(nwg, min(nb, tc_env_int("RLAOPT_B200_TC_NB", nb)));
     int la = nb >= 4 ? 2 : 1;
     la = max(1, min(nb >= 3 ? nb - 2 : 1, tc_env_int("RLAOPT_B200_TC_LA", la)));
     // smem: A ring (column-tile images) + V ring (la stages deeper: V of tile t is consumed la tiles after its A)
-    const size_t a_stage = tc_image_bytes(kb), v_stage = tc_v_stage_bytes(kp);
+    const size_t a_stage = wide ? (size_t)TC_WIDE_STAGE_BYTES : tc_image_bytes(kb), v_stage = tc_v_stage_bytes(kp);
     const size_t fixed = 8 * TC_BM * sizeof(float) + 64 * sizeof(uint64_t) + 64;
-    int sa = 4;
-    while (sa > 2 && sa * a_stage + (sa + la) * v_stage + fixed > (size_t)TC_SMEM_LIMIT) --sa;
-    int sv = sa + la;
+    int sa = 4, sv;
+    if (wide) {  // V images of two segments (4 tiles) in flight, the rest of smem for 64 KB K-block slots
+        sv = 4;
+        sa = 3;
+        while (sa > 2 && sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) --sa;
+    } else {
+        while (sa > 2 && sa * a_stage + (sa + la) * v_stage + fixed > (size_t)TC_SMEM_LIMIT) --sa;
+        sv = sa + la;
+    }
     if (sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) return false;
     if (2 * sa + 2 * sv + 3 * nb + 2 * 3 + 1 > 64) return false;
     pl->kb = kb;
@@ -1135,13 +1256,14 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     pl->nb = nb;
     pl->nwg = nwg;
     pl->la = la;
+    pl->wide = wide ? 1 : 0;
     pl->sub_tiles = (m + TC_BN - 1) / TC_BN;
     // CTA pairs (clusters of two row blocks sharing every column-tile load through multicast): +3 % under the
     // power cap at C2.  Default: on once the launch has at least two waves of row blocks; RLAOPT_B200_TC_PAIR=0/1 forces.
     {
         const int64_t row_blocks = (n + TC_BM - 1) / TC_BM;
         const int want = tc_env_int("RLAOPT_B200_TC_PAIR", -1);
-        pl->pair = row_blocks >= 2 && (want < 0 ? row_blocks >= 2 * (int64_t)sm_count : want != 0);
+        pl->pair = !wide && row_blocks >= 2 && (want < 0 ? row_blocks >= 2 * (int64_t)sm_count : want != 0);
     }
     pl->smem_bytes = sa * a_stage + sv * v_stage + fixed;
     const int64_t base = ((n + TC_BM - 1) / TC_BM) * pl->k_chunks;
@@ -1186,7 +1308,7 @@ extern "C" int kmm_tc_prof_read(long long* host64) {
 }
 #endif
 
-bool tc_supported_d(int64_t d) { return d >= 1 && d <= TC_MAX_D; }
+bool tc_supported_d(int64_t d) { return d >= 1 && d <= TC_MAX_D_WIDE; }
 bool tc_supported_k(int64_t k) { return k >= 1; }
 
 size_t tc_packed_bytes(int64_t n, int64_t d) {
@@ -1273,6 +1395,7 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     p.la = pl.la;
     p.diag = tc_env_int("RLAOPT_B200_TC_DIAG", 0);
     p.pair = pl.pair;
+    p.wide = pl.wide;
     p.kid = kid;
     p.sub_tiles = pl.sub_tiles;
     p.tiles_per_split = pl.tiles_per_split;

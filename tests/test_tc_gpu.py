@@ -31,7 +31,8 @@ def test_layout_selection(dev):
     f32, f64 = torch.float32, torch.float64
     assert ops.choose_layout(ops.KERNEL_IDS["rbf"], f32, 128, 64) == LAYOUT_TC
     assert ops.choose_layout(ops.KERNEL_IDS["matern52"], f32, 3, 1) == LAYOUT_TC
-    assert ops.choose_layout(ops.KERNEL_IDS["rbf"], f32, 500, 10) == LAYOUT_SIMT  # d > 192
+    assert ops.choose_layout(ops.KERNEL_IDS["rbf"], f32, 500, 10) == LAYOUT_TC  # wide-d variant (K-blocks through smem)
+    assert ops.choose_layout(ops.KERNEL_IDS["rbf"], f32, 3000, 10) == LAYOUT_SIMT  # d > 2048
     assert ops.choose_layout(ops.KERNEL_IDS["rbf"], f64, 128, 64) == LAYOUT_SIMT  # fp64
     assert ops.choose_layout(ops.KERNEL_IDS["laplace"], f32, 32, 16) == LAYOUT_SIMT  # L1 distance
     assert ops.choose_layout(ops.KERNEL_IDS["matern12"], f32, 32, 16) == LAYOUT_TC  # near pairs recomputed exactly
@@ -232,3 +233,22 @@ def test_matern12_diagonal_is_exact(dev):
     Y = kernel_matmat(X, X, torch.eye(n, device=dev), "matern12", 0.05, layout=LAYOUT_TC)
     assert torch.equal(Y.diagonal(), torch.ones(n, device=dev))
     assert float((Y - torch.eye(n, device=dev)).abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize("name", TC_KERNELS)
+@pytest.mark.parametrize("n,m,d,k", [(300, 500, 193, 3), (129, 1000, 256, 64), (1000, 70, 500, 10), (257, 4100, 784, 1),
+                                     (64, 64, 1000, 16), (2000, 2000, 320, 33), (128, 129, 2048, 2)])
+def test_wide_feature_variant(dev, name, n, m, d, k):
+    """d > 192: X no longer fits TMEM; MMA1 accumulates S over 64-feature K-blocks streamed through smem (two column
+    tiles per segment).  Odd tile counts leave a phantom second tile in the last segment."""
+    from rlaopt_b200._lib import LAYOUT_TC
+    from rlaopt_b200.ops import kernel_matmat
+
+    A1, A2 = _rand((n, d), 41) / d**0.5, _rand((m, d), 42) / d**0.5
+    V, W = _rand((m, k), 43), _rand((n, k), 44)
+    ref = ko.kernel_matmat_gemm_form(A1, A2, V, name, 1.1, 0.5, dtype=torch.float64)
+    got = kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), name, 1.1, 0.5, layout=LAYOUT_TC)
+    assert ko.rel_fro_error(got, ref) <= 1e-5, (name, n, m, d, k, ko.rel_fro_error(got, ref))
+    ref_t = ko.kernel_matmat_gemm_form(A2, A1, W, name, 1.1, 0.5, dtype=torch.float64)
+    got_t = kernel_matmat(A1.to(dev), A2.to(dev), W.to(dev), name, 1.1, 0.5, transpose=True, layout=LAYOUT_TC)
+    assert ko.rel_fro_error(got_t, ref_t) <= 1e-5
