@@ -599,8 +599,15 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                         mbar_wait(&v_empty[sv], phv);
                         unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
                         mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
-                        bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
-                        bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
+                        if (!p.pair) {
+                            bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
+                            bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
+                        } else if (crank == 0) {
+                            bulk_copy_g2s_mc(vdst, v_src, KP * 128, &v_full[sv], 3);
+                            bulk_copy_g2s_mc(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv], 3);
+                        } else {
+                            bulk_copy_g2s_mc(vdst + KP * 128, v_src + KP * 128, KP * 128 + 16, &v_full[sv], 3);
+                        }
                         v_src += v_img_bytes;
                         n_src += TC_BN;
                         if (++sv == SV) {
@@ -621,8 +628,15 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                         }
                         for (int e = 0; e < cnt; ++e) {
                             const unsigned char* y_img = a_src + (size_t)e * a_img_bytes + koff;
-                            bulk_copy_g2s(dst + (4 + e) * TC_KBLOCK_BYTES, y_img, TC_KBLOCK_BYTES, &a_full[sa]);
-                            bulk_copy_g2s(dst + (6 + e) * TC_KBLOCK_BYTES, y_img + lo_img, TC_KBLOCK_BYTES, &a_full[sa]);
+                            if (!p.pair) {
+                                bulk_copy_g2s(dst + (4 + e) * TC_KBLOCK_BYTES, y_img, TC_KBLOCK_BYTES, &a_full[sa]);
+                                bulk_copy_g2s(dst + (6 + e) * TC_KBLOCK_BYTES, y_img + lo_img, TC_KBLOCK_BYTES, &a_full[sa]);
+                            } else if ((uint32_t)e == crank || cnt == 1 && crank == 0) {
+                                // CTA pair: the two CTAs have different rows (own X) but the same columns -- each fetches
+                                // one of the segment's two Y tiles and multicasts it to both
+                                bulk_copy_g2s_mc(dst + (4 + e) * TC_KBLOCK_BYTES, y_img, TC_KBLOCK_BYTES, &a_full[sa], 3);
+                                bulk_copy_g2s_mc(dst + (6 + e) * TC_KBLOCK_BYTES, y_img + lo_img, TC_KBLOCK_BYTES, &a_full[sa], 3);
+                            }
                         }
                         if (++sa == SA) {
                             sa = 0;
@@ -780,7 +794,10 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                                 }
                             }
                             __syncwarp();
-                            if (elect_one()) umma_commit(&a_empty[sa]);
+                            if (elect_one()) {
+                                if (p.pair) umma_commit_mc(&a_empty[sa], 3);
+                                else umma_commit(&a_empty[sa]);
+                            }
                             __syncwarp();
                             if (++sa == SA) {
                                 sa = 0;
@@ -1263,7 +1280,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     {
         const int64_t row_blocks = (n + TC_BM - 1) / TC_BM;
         const int want = tc_env_int("RLAOPT_B200_TC_PAIR", -1);
-        pl->pair = !wide && row_blocks >= 2 && (want < 0 ? row_blocks >= 2 * (int64_t)sm_count : want != 0);
+        pl->pair = row_blocks >= 2 && (want < 0 ? row_blocks >= 2 * (int64_t)sm_count : want != 0);
     }
     pl->smem_bytes = sa * a_stage + sv * v_stage + fixed;
     const int64_t base = ((n + TC_BM - 1) / TC_BM) * pl->k_chunks;
