@@ -588,33 +588,13 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             uint32_t pha = 1, phv = 1;  // a fresh barrier passes a wait on parity 1
             const uint32_t crank = p.pair ? cluster_ctarank() : 0;
             if (p.wide) {
-                // Wide d: per segment of two column tiles, first their V images, then one A-ring slot per 64-feature
-                // K-block: {X hi, X lo} of this CTA's 128 rows and {Y hi, Y lo} of the segment's 128 columns.
+                // Wide d: per segment of two column tiles one A-ring slot per 64-feature K-block, then their V images;
+                // a slot holds {X hi, X lo} of this CTA's 128 rows and {Y hi, Y lo} of the segment's 128 columns.
                 const bool rows_live = row0 < tc_npad(p.n);
                 const unsigned char* x_img = p.rows + tc_image_offset(p.n) + (size_t)(row0 >> 6) * a_img_bytes;
                 const size_t lo_img = (size_t)KB * TC_KBLOCK_BYTES;
                 for (int u0 = 0; u0 < T; u0 += 2) {
                     const int cnt = (u0 + 1 < T) ? 2 : 1;
-                    for (int e = 0; e < cnt; ++e) {
-                        mbar_wait(&v_empty[sv], phv);
-                        unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
-                        mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
-                        if (!p.pair) {
-                            bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
-                            bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
-                        } else if (crank == 0) {
-                            bulk_copy_g2s_mc(vdst, v_src, KP * 128, &v_full[sv], 3);
-                            bulk_copy_g2s_mc(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv], 3);
-                        } else {
-                            bulk_copy_g2s_mc(vdst + KP * 128, v_src + KP * 128, KP * 128 + 16, &v_full[sv], 3);
-                        }
-                        v_src += v_img_bytes;
-                        n_src += TC_BN;
-                        if (++sv == SV) {
-                            sv = 0;
-                            phv ^= 1;
-                        }
-                    }
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&a_empty[sa], pha);
                         unsigned char* dst = a_ring + (size_t)sa * a_stage_bytes;
@@ -641,6 +621,27 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                         if (++sa == SA) {
                             sa = 0;
                             pha ^= 1;
+                        }
+                    }
+                    // V images and column norms of the segment: needed only after its pointwise stage
+                    for (int e = 0; e < cnt; ++e) {
+                        mbar_wait(&v_empty[sv], phv);
+                        unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
+                        mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
+                        if (!p.pair) {
+                            bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
+                            bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
+                        } else if (crank == 0) {
+                            bulk_copy_g2s_mc(vdst, v_src, KP * 128, &v_full[sv], 3);
+                            bulk_copy_g2s_mc(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv], 3);
+                        } else {
+                            bulk_copy_g2s_mc(vdst + KP * 128, v_src + KP * 128, KP * 128 + 16, &v_full[sv], 3);
+                        }
+                        v_src += v_img_bytes;
+                        n_src += TC_BN;
+                        if (++sv == SV) {
+                            sv = 0;
+                            phv ^= 1;
                         }
                     }
                     a_src += (size_t)cnt * a_img_bytes;
@@ -1237,7 +1238,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     while (kp < 64 && kp < k) kp *= 2;
     // k > 64: 128-column chunks halve the number of times S and the pointwise stage are recomputed; they need
     // 256 TMEM columns for the two O buffers, which leaves two S/P buffers for d <= 128
-    if (!wide && k > 64 && 64 * kb + 2 * 64 + 2 * 128 <= 512 && tc_env_int("RLAOPT_B200_TC_KP128", 1)) kp = 128;
+    if (k > 64 && (wide ? 0 : 64 * kb) + (wide ? 4 : 2) * 64 + 2 * 128 <= 512 && tc_env_int("RLAOPT_B200_TC_KP128", 1)) kp = 128;
     // Small d and k: the tensor work per tile is small and the kernel is bound by the pointwise stage (MUFU, TMEM
     // and mbarrier latencies); a third epilogue warpgroup keeps three tiles in flight per SM sub-partition.
     int nwg = (kb <= 2 && kp <= 32 && tc_env_int("RLAOPT_B200_TC_NWG", 3) == 3) ? 3 : 2;
@@ -1255,8 +1256,8 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     const size_t a_stage = wide ? (size_t)TC_WIDE_STAGE_BYTES : tc_image_bytes(kb), v_stage = tc_v_stage_bytes(kp);
     const size_t fixed = 8 * TC_BM * sizeof(float) + 64 * sizeof(uint64_t) + 64;
     int sa = 4, sv;
-    if (wide) {  // V images of two segments (4 tiles) in flight, the rest of smem for 64 KB K-block slots
-        sv = 4;
+    if (wide) {  // V images of one or two segments in flight, the rest of smem for 64 KB K-block slots
+        sv = kp > 64 ? 2 : 4;
         sa = 3;
         while (sa > 2 && sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) --sa;
     } else {

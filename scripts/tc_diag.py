@@ -174,7 +174,7 @@ if __name__ == "__main__":
         from rlaopt_b200.kernels import KernelConfig
         for name, n, d, k in (("LaplaceLinOp", 131072, 32, 16), ("Matern12LinOp", 131072, 32, 16), ("Matern32LinOp", 262144, 32, 16),
                               ("Matern52LinOp", 262144, 32, 16), ("RBFLinOp", 262144, 32, 16), ("LaplaceLinOp", 65536, 128, 64),
-                              ("RBFLinOp", 131072, 64, 128), ("RBFLinOp", 131072, 64, 1000), ("RBFLinOp", 131072, 16, 1), ("RBFLinOp", 131072, 8, 10), ("RBFLinOp", 131072, 128, 16), ("RBFLinOp", 131072, 100, 1), ("RBFLinOp", 65536, 256, 16), ("RBFLinOp", 65536, 784, 1), ("Matern52LinOp", 32768, 1024, 64)):
+                              ("RBFLinOp", 131072, 64, 128), ("RBFLinOp", 131072, 64, 1000), ("RBFLinOp", 131072, 16, 1), ("RBFLinOp", 131072, 8, 10), ("RBFLinOp", 131072, 128, 16), ("RBFLinOp", 131072, 100, 1), ("RBFLinOp", 65536, 256, 16), ("RBFLinOp", 65536, 784, 1), ("Matern52LinOp", 32768, 1024, 64), ("RBFLinOp", 32768, 784, 200)):
             X = (rnd((n, d), 1) / d**0.5).to(dev)
             V = rnd((n, k), 2).to(dev)
             op = getattr(K, name)(X, X, KernelConfig(lengthscale=1.0))

@@ -237,7 +237,7 @@ def test_matern12_diagonal_is_exact(dev):
 
 @pytest.mark.parametrize("name", TC_KERNELS)
 @pytest.mark.parametrize("n,m,d,k", [(300, 500, 193, 3), (129, 1000, 256, 64), (1000, 70, 500, 10), (257, 4100, 784, 1),
-                                     (64, 64, 1000, 16), (2000, 2000, 320, 33), (128, 129, 2048, 2)])
+                                     (64, 64, 1000, 16), (2000, 2000, 320, 33), (128, 129, 2048, 2), (300, 900, 400, 130), (200, 3000, 256, 200)])
 def test_wide_feature_variant(dev, name, n, m, d, k):
     """d > 192: X no longer fits TMEM; MMA1 accumulates S over 64-feature K-blocks streamed through smem (two column
     tiles per segment).  Odd tile counts leave a phantom second tile in the last segment."""
