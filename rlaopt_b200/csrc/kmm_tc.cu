@@ -936,17 +936,19 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             mbar_wait(&o_full[ob], par);
             tc_fence_after();
             const uint64_t d2 = pack2(dsc, dsc);
+            constexpr int W = DW < 32 ? DW : 32;
+            constexpr int NLD = DW / W;  // 1 or 2 loads in flight, one wait (a tcgen05.ld round trip is ~180 cycles)
+            uint32_t o[NLD][W];
 #pragma unroll
-            for (int c0 = 0; c0 < DW; c0 += 32) {
-                constexpr int W = DW < 32 ? DW : 32;
-                uint32_t o[W];
-                tmem_ld_n<W>(tmem + lane_bits + col_o + ob * KP + (SPLIT ? g * DW : 0) + c0, o);
-                tmem_wait_ld();
-                if (!(p.diag & 4))
+            for (int l = 0; l < NLD; ++l) tmem_ld_n<W>(tmem + lane_bits + col_o + ob * KP + (SPLIT ? g * DW : 0) + l * W, o[l]);
+            tmem_wait_ld();
+            if (!(p.diag & 4))
+#pragma unroll
+            for (int l = 0; l < NLD; ++l)
 #pragma unroll
                 for (int e = 0; e < W / 2; ++e)
-                    acc[c0 / 2 + e] = fma2(pack2(__uint_as_float(o[2 * e]), __uint_as_float(o[2 * e + 1])), d2, acc[c0 / 2 + e]);
-            }
+                    acc[l * (W / 2) + e] = fma2(pack2(__uint_as_float(o[l][2 * e]), __uint_as_float(o[l][2 * e + 1])), d2,
+                                                acc[l * (W / 2) + e]);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_free[ob]);
