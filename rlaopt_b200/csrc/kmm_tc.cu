@@ -504,7 +504,9 @@ __host__ __device__ constexpr uint32_t tc_v_stage_bytes(int kp) { return (uint32
 //                                P_hi (32 columns of fp16 pairs) | P_lo (32 columns)
 //   [64 KB + 64 NB, +2 KP)       two O buffers (one fresh accumulator per sub-tile, alternating)
 // M12: instantiation for Matern-1/2 (carries the near-point recompute; the other kernels stay free of its code)
-template <int KP, int NWG, bool M12>
+// WIDE: d > 192 instantiation (K-block streaming MMA1); kept out of the common kernels, whose C2 throughput drops
+// by 2 % when that code shares their instruction footprint
+template <int KP, int NWG, bool M12, bool WIDE>
 __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcParams p) {
     constexpr int TC_EPI_WARPS = NWG * 4;
     constexpr int NOB = NWG;  // O buffers: one per epilogue warpgroup (tile u accumulates into O[u % NWG])
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = p.kb, SA = p.a_stages, SV = p.v_stages, NB = p.nb;
     const uint32_t a_img_bytes = (uint32_t)tc_image_bytes(KB);  // hi + lo image of one 64-point tile in HBM
-    const uint32_t a_stage_bytes = p.wide ? TC_WIDE_STAGE_BYTES : a_img_bytes;  // one slot of the A ring
+    const uint32_t a_stage_bytes = WIDE ? TC_WIDE_STAGE_BYTES : a_img_bytes;  // one slot of the A ring
     constexpr uint32_t v_img_bytes = KP * 256 + 16;             // hi + lo + trailer, as stored in HBM
     constexpr uint32_t v_stage_bytes = tc_v_stage_bytes(KP);
     constexpr uint32_t v_norm_off = KP * 256 + 16;
@@ -566,7 +568,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     if (p.pair) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t x_cols = p.wide ? 0 : KB * 64;  // wide-d: X is not resident in TMEM
+    const uint32_t x_cols = WIDE ? 0 : KB * 64;  // wide-d: X is not resident in TMEM
     const uint32_t col_a_hi = 0, col_a_lo = KB * 32, col_sp = x_cols, col_o = x_cols + NB * 64;
 
     const TcHeader* rh = reinterpret_cast<const TcHeader*>(p.rows);
@@ -587,7 +589,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             int sa = 0, sv = 0;
             uint32_t pha = 1, phv = 1;  // a fresh barrier passes a wait on parity 1
             const uint32_t crank = p.pair ? cluster_ctarank() : 0;
-            if (p.wide) {
+            if constexpr (WIDE) {
                 // Wide d: per segment of two column tiles one A-ring slot per 64-feature K-block, then their V images;
                 // a slot holds {X hi, X lo} of this CTA's 128 rows and {Y hi, Y lo} of the segment's 128 columns.
                 const bool rows_live = row0 < tc_npad(p.n);
@@ -765,7 +767,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             // MMA2 as far as the NB S/P buffers and the A ring allow; while one of them polls its barriers the
             // other's instructions keep the tensor pipe fed ----
             const int par = (warp == TC_EPI_WARPS + 1) ? 0 : 1;
-            if (p.wide) {
+            if constexpr (WIDE) {
                 // Wide d (warp 9 only): S[b0], S[b0 + 1] of a two-tile segment accumulate over the K-blocks with
                 // M128 x N128 x K16 MMAs, both operands from the A-ring slot (SS mode runs at the full rate for N = 128)
                 if (par == 0) {
@@ -892,7 +894,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         const float m2c = -2.0f * rh->inv_scale * ch->inv_scale;
 
         // ---- X tile -> TMEM (warpgroup 0: hi halves, warpgroup 1: lo halves) ----
-        if (h < 2 && !p.wide) {
+        if (h < 2 && !WIDE) {
             const unsigned char* img = p.rows + tc_image_offset(p.n) + (size_t)(grow >> 6) * a_img_bytes +
                                        (size_t)h * KB * TC_KBLOCK_BYTES;
             const int r = (int)(grow & 63);
@@ -1356,9 +1358,9 @@ size_t tc_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int sm_cou
     return round_up((int64_t)pl.vimg_bytes, 256) + pl.part_bytes;
 }
 
-template <int KP, int NWG, bool M12>
+template <int KP, int NWG, bool M12, bool WIDE>
 static cudaError_t launch_tc_inst(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
-    auto kern = kmm_tc_kernel<KP, NWG, M12>;
+    auto kern = kmm_tc_kernel<KP, NWG, M12, WIDE>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (err != cudaSuccess) return err;
     unsigned row_blocks = (unsigned)((n + TC_BM - 1) / TC_BM);
@@ -1380,8 +1382,13 @@ static cudaError_t launch_tc_inst(const TcParams& p, const TcPlan& pl, int64_t n
 
 template <int KP, int NWG>
 static cudaError_t launch_tc_kp(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
-    return p.kid == KID_MATERN12 ? launch_tc_inst<KP, NWG, true>(p, pl, n, stream)
-                                 : launch_tc_inst<KP, NWG, false>(p, pl, n, stream);
+    if constexpr (NWG == 2) {
+        if (p.wide)
+            return p.kid == KID_MATERN12 ? launch_tc_inst<KP, NWG, true, true>(p, pl, n, stream)
+                                         : launch_tc_inst<KP, NWG, false, true>(p, pl, n, stream);
+    }
+    return p.kid == KID_MATERN12 ? launch_tc_inst<KP, NWG, true, false>(p, pl, n, stream)
+                                 : launch_tc_inst<KP, NWG, false, false>(p, pl, n, stream);
 }
 
 cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packed, int64_t m, int64_t d,
