@@ -414,10 +414,12 @@ __global__ void __launch_bounds__(256) tc_pack_v_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------
 #ifdef KMM_TC_PROFILE
 __device__ long long g_tc_prof[64];
+#define TC_DIAG(bit) ((p.diag & (bit)) != 0)  // RLAOPT_B200_TC_DIAG knock-outs exist in the profile build only
 #define TC_PROF_DECL long long prof_t = clock64(); long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define TC_PROF(i) { const long long now_ = clock64(); prof_acc[i] += now_ - prof_t; prof_t = now_; }
 #define TC_PROF_FLUSH(base) if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) { for (int i_ = 0; i_ < 8; ++i_) g_tc_prof[(base) + i_] = prof_acc[i_]; }
 #else
+#define TC_DIAG(bit) false
 #define TC_PROF_DECL
 #define TC_PROF(i) {}
 #define TC_PROF_FLUSH(base) {}
@@ -435,7 +437,7 @@ struct TcParams {
     int nb, la;              // S/P buffers in TMEM, MMA1 look-ahead (tiles)
     int wide;                // 1: d > 192, feature-chunked MMA1 with X and Y K-blocks streamed through the A ring
     int pair;                // 1: launched as clusters of two CTAs that share every column-tile load (multicast halves)
-    int diag;                // RLAOPT_B200_TC_DIAG knock-outs (profiling only): 1 no MMA, 2 no pointwise, 4 no drain, 8 no loads
+    int diag;                // RLAOPT_B200_TC_DIAG knock-outs (-DKMM_TC_PROFILE build only): 1 no MMA, 2 no pointwise, 4 no drain, 8 no loads
     float scale_out;
     int64_t sub_tiles;        // ceil(m / 64)
     int tiles_per_split;
@@ -651,7 +653,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             } else
             for (int u = 0; u < T; ++u) {
                 mbar_wait(&a_empty[sa], pha);
-                if (p.diag & 8) {
+                if (TC_DIAG(8)) {
                     mbar_arrive(&a_full[sa]);
                     mbar_wait(&v_empty[sv], phv);
                     mbar_arrive(&v_full[sv]);
@@ -714,7 +716,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             const uint32_t img = a_ring_base + (uint32_t)s * a_img_bytes;
             const uint32_t dlo_hi = desc_lo0 + (img >> 4);             // Y hi image
             const uint32_t dlo_lo = desc_lo0 + ((img + lo_off) >> 4);  // Y lo image
-            if (!(p.diag & 1) && elect_one()) {
+            if (!TC_DIAG(1) && elect_one()) {
                 uint32_t acc = 0;
 #pragma unroll 1
                 for (int part = 0; part < 3; ++part) {
@@ -748,7 +750,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             const uint32_t img = v_ring_base + (uint32_t)s * v_stage_bytes;
             const uint32_t dlo_hi = desc_lo0 + (img >> 4);
             const uint32_t dlo_lo = desc_lo0 + ((img + KP * 128) >> 4);
-            if (!(p.diag & 1) && elect_one()) {
+            if (!TC_DIAG(1) && elect_one()) {
 #pragma unroll
                 for (int part = 0; part < 3; ++part) {
                     const uint32_t a = (part == 1 ? p_lo : p_hi);
@@ -787,7 +789,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                             const uint32_t yh = desc_lo0 + ((st + 4 * TC_KBLOCK_BYTES) >> 4);
                             const uint32_t yl = desc_lo0 + ((st + 6 * TC_KBLOCK_BYTES) >> 4);
                             const int steps = min(4, nk1 - 4 * kb);
-                            if (!(p.diag & 1) && elect_one()) {
+                            if (!TC_DIAG(1) && elect_one()) {
 #pragma unroll 1
                                 for (int part = 0; part < 3; ++part) {
                                     const uint32_t ad = (part == 1 ? xl : xh), bd = (part == 0 ? yl : yh);
@@ -944,7 +946,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
 #pragma unroll
             for (int l = 0; l < NLD; ++l) tmem_ld_n<W>(tmem + lane_bits + col_o + ob * KP + (SPLIT ? g * DW : 0) + l * W, o[l]);
             tmem_wait_ld();
-            if (!(p.diag & 4))
+            if (!TC_DIAG(4))
 #pragma unroll
             for (int l = 0; l < NLD; ++l)
 #pragma unroll
@@ -994,7 +996,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             TC_PROF(2)
             const float4* nyv = reinterpret_cast<const float4*>(vst + v_norm_off);
             const float vinv = *reinterpret_cast<const float*>(vst + KP * 256);
-            if (p.diag & 2) {
+            if (TC_DIAG(2)) {
                 uint32_t phi[16], plo[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) phi[i] = s0[i] + s1[i], plo[i] = s0[16 + i] + s1[16 + i];
@@ -1167,7 +1169,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             drain_through(T - 1);
         } else {
             const int last = ((T - 1 - g) / NWG) * NWG + g;  // this warpgroup's last tile (T > g)
-            if (T > g) drain(g, (uint32_t)((last / NWG) & 1), (p.diag & 2) ? 1.0f : dsc_prev);
+            if (T > g) drain(g, (uint32_t)((last / NWG) & 1), TC_DIAG(2) ? 1.0f : dsc_prev);
         }
 
         if (SPLIT) {
