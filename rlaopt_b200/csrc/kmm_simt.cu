@@ -20,7 +20,13 @@ namespace {
 constexpr int BM = 128;  // output rows per CTA
 constexpr int BN = 64;   // K columns per step
 constexpr int DC = PACK_FEATS;  // features staged per cp.async stage
-constexpr int NT = 256;  // threads per CTA (16 x 16)
+// threads per CTA: every thread owns an 8 x TN block of the 128 x 64 distance tile; TN = 8 for fp32 with up to 32
+// columns of V per chunk (128 threads: half the shared-memory loads and loop overhead per FADD), else 4 (256 threads)
+template <typename T, int KC>
+struct SimtShape {
+    static constexpr int TN = (sizeof(T) == 4 && KC <= 32) ? 8 : 4;  // KC = 64 keeps 8 x 4 (64 phase-2 accumulators per thread otherwise)
+    static constexpr int NT = BM * BN / (8 * TN);
+};
 constexpr int FLUSH_TILES = 16;
 
 template <typename T, int KC>
@@ -29,7 +35,7 @@ struct alignas(16) SimtSmem {
     T Bs[2][DC][BN];
     T Ps[BN][BM];  // P^T, 16-byte chunks XOR-swizzled by (j >> 2) & 7
     T Vs[BN][KC];
-    T Yt[BM * KC / NT][NT];  // second-level accumulators, one private column per thread
+    T Yt[BM * KC / SimtShape<T, KC>::NT][SimtShape<T, KC>::NT];  // second-level accumulators, one private column per thread
 };
 
 template <typename T, int N>
@@ -64,7 +70,7 @@ template <>
 __device__ __forceinline__ double fmadd<double>(double a, double b, double c) { return fma(a, b, c); }
 
 template <typename T, bool L1, int KC>
-__global__ void __launch_bounds__(NT, sizeof(T) == 4 ? 2 : 1)
+__global__ void __launch_bounds__(SimtShape<T, KC>::NT, sizeof(T) == 4 ? (KC <= 32 ? 3 : 2) : 1)
 kmm_simt_kernel(const T* __restrict__ Rt, int64_t n, int64_t n_pad,
                 const T* __restrict__ Ct, int64_t m, int64_t m_pad, int d_pad,
                 const T* __restrict__ V, int64_t ldv, int k, int v_vec_ok,
@@ -74,13 +80,14 @@ kmm_simt_kernel(const T* __restrict__ Rt, int64_t n, int64_t n_pad,
     SimtSmem<T, KC>& sm = *reinterpret_cast<SimtSmem<T, KC>*>(smem_raw);
 
     constexpr int VEC = 16 / sizeof(T);
-    constexpr int RT = KC / 8;  // phase-2 rows per thread
-    constexpr int CT = 4;       // phase-2 columns per thread
-    constexpr int NACC = RT * CT;
-    static_assert(BM * KC / NT == NACC, "phase-2 tiling must cover the output tile");
+    constexpr int TN = SimtShape<T, KC>::TN, NT = SimtShape<T, KC>::NT;
+    constexpr int CT = 4;                 // phase-2 columns per thread
+    constexpr int NACC = BM * KC / NT;    // phase-2 accumulators per thread
+    constexpr int RT = NACC / CT;         // phase-2 rows per thread
+    static_assert(RT >= 1 && RT * CT == NACC, "phase-2 tiling must cover the output tile");
 
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
     const int64_t row0 = (int64_t)blockIdx.x * BM;
     const int kc0 = blockIdx.y * KC;
     const int64_t n_col_tiles = (m + BN - 1) / BN;
@@ -148,11 +155,11 @@ kmm_simt_kernel(const T* __restrict__ Rt, int64_t n, int64_t n_pad,
     int since_flush = 0;
     for (int64_t t = t_begin; t < t_end; ++t) {
         // ---------------- phase 1: distances ----------------
-        T S[8][4];
+        T S[8][TN];
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) S[r][c] = T(0);
+            for (int c = 0; c < TN; ++c) S[r][c] = T(0);
 
         for (int c = 0; c < nd; ++c) {
             cp_async_wait_all();
@@ -164,13 +171,13 @@ kmm_simt_kernel(const T* __restrict__ Rt, int64_t n, int64_t n_pad,
 #pragma unroll
             for (int dd = 0; dd < DC; ++dd) {
                 alignas(16) T a[8];
-                alignas(16) T b[4];
+                alignas(16) T b[TN];
                 lds_vec<T, 8>(a, &sm.As[buf][dd][ty * 8]);
-                lds_vec<T, 4>(b, &sm.Bs[buf][dd][tx * 4]);
+                lds_vec<T, TN>(b, &sm.Bs[buf][dd][tx * TN]);
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
+                    for (int cc = 0; cc < TN; ++cc) {
                         const T diff = a[r] - b[cc];
                         if constexpr (L1) S[r][cc] += absval<T>(diff);
                         else S[r][cc] = fmadd<T>(diff, diff, S[r][cc]);
@@ -179,10 +186,10 @@ kmm_simt_kernel(const T* __restrict__ Rt, int64_t n, int64_t n_pad,
         }
 
         // ---------------- pointwise: P = f(S) -> swizzled smem ----------------
-        pointwise_tile<T, 8, 4>(kid, S);
+        pointwise_tile<T, 8, TN>(kid, S);
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int j = tx * 4 + cc;
+        for (int cc = 0; cc < TN; ++cc) {
+            const int j = tx * TN + cc;
             const int swz = (j >> 2) & 7;
             alignas(16) T p[8];
 #pragma unroll
@@ -274,7 +281,7 @@ cudaError_t launch_one(const SimtArgs<T>& a, int splits, int tiles_per_split, T*
     const int k_chunks = (int)((a.k + KC - 1) / KC);
     dim3 grid((unsigned)row_tiles, (unsigned)k_chunks, (unsigned)splits);
     const int v_vec_ok = ((reinterpret_cast<uintptr_t>(a.V) % 16) == 0) && ((a.ldv * sizeof(T)) % 16 == 0);
-    kern<<<grid, NT, sizeof(Smem), a.stream>>>(a.Rt, a.n, a.n_pad, a.Ct, a.m, a.m_pad, (int)a.d_pad, a.V, a.ldv,
+    kern<<<grid, SimtShape<T, KC>::NT, sizeof(Smem), a.stream>>>(a.Rt, a.n, a.n_pad, a.Ct, a.m, a.m_pad, (int)a.d_pad, a.V, a.ldv,
                                                (int)a.k, v_vec_ok, out, ldo, split_stride, scale, a.kid,
                                                tiles_per_split);
     return cudaGetLastError();
