@@ -168,7 +168,9 @@ kmm_simt_kernel(const T* __restrict__ Rt, int64_t n, int64_t n_pad,
             if (c + 1 < nd) load_ab(t, c + 1, (c + 1) & 1);
             cp_async_commit();
             const int buf = c & 1;
-#pragma unroll
+            // the 8 x 8 tile fully unrolled over a chunk is 16 KB of FADDs (ncu: 8 % instruction-fetch stalls): unroll by 2
+            constexpr int UNR = TN == 8 ? 2 : DC;
+#pragma unroll(UNR)
             for (int dd = 0; dd < DC; ++dd) {
                 alignas(16) T a[8];
                 alignas(16) T b[TN];
