@@ -73,6 +73,15 @@ def test_host_only_entry_points(lib):
     # Laplace (L1) and fp64 never run on the tensor-core layout
     assert lib.rlaopt_b200_layout_supported(1, 4, 128, 64, LAYOUT_TC) == 0
     assert lib.rlaopt_b200_layout_supported(0, 8, 128, 64, LAYOUT_TC) == 0
+    # the four L2-distance kernels in fp32: tensor-core layout up to d = 2048 (X in TMEM up to 192, K-block streaming beyond)
+    for kid in (0, 2, 3, 4):
+        for d in (1, 128, 192, 193, 784, 2048):
+            assert lib.rlaopt_b200_layout_supported(kid, 4, d, 1, LAYOUT_TC) == 1
+        assert lib.rlaopt_b200_layout_supported(kid, 4, 2049, 1, LAYOUT_TC) == 0
+    # TC pack: 256 B header + one fp32 norm per padded point + (hi | lo) fp16 images of 64 points x 64-feature K-blocks
+    assert lib.rlaopt_b200_packed_bytes(10, 3, 4, LAYOUT_TC) == 256 + 128 * 4 + 2 * (2 * 64 * 128)
+    assert lib.rlaopt_b200_packed_bytes(129, 130, 4, LAYOUT_TC) == 256 + 256 * 4 + 4 * (2 * 3 * 64 * 128)
+    assert lib.rlaopt_b200_packed_bytes(10, 3, 8, LAYOUT_TC) == 0
 
 
 def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
