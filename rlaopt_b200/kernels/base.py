@@ -51,17 +51,33 @@ class _PackCache:
     def __init__(self, A1: torch.Tensor, A2: torch.Tensor, lengthscale):
         self.A1, self.A2, self.lengthscale = A1, A2, lengthscale
         self.shared = _same_storage(A1, A2)
-        self._packs: dict[int, tuple] = {}
+        self._rows: dict[int, object] = {}
+        self._cols: dict[int, object] = {}
+
+    def rows(self, layout: int):
+        """Pack of A1 (built on first use; shared with the column pack when A1 is A2)."""
+        if layout not in self._rows:
+            if self.shared and layout in self._cols:
+                self._rows[layout] = self._cols[layout]
+            else:
+                self._rows[layout] = ops.pack_points(self.A1, self.lengthscale, None, layout)
+        return self._rows[layout]
+
+    def cols(self, layout: int):
+        """Pack of A2 alone -- all a row oracle needs (its rows are gathered per block)."""
+        if layout not in self._cols:
+            if self.shared and layout in self._rows:
+                self._cols[layout] = self._rows[layout]
+            else:
+                self._cols[layout] = ops.pack_points(self.A2, self.lengthscale, None, layout)
+        return self._cols[layout]
 
     def get(self, layout: int):
-        if layout not in self._packs:
-            P1 = ops.pack_points(self.A1, self.lengthscale, None, layout)
-            P2 = P1 if self.shared else ops.pack_points(self.A2, self.lengthscale, None, layout)
-            self._packs[layout] = (P1, P2)
-        return self._packs[layout]
+        return self.rows(layout), self.cols(layout)
 
     def clear(self) -> None:
-        self._packs.clear()
+        self._rows.clear()
+        self._cols.clear()
 
 
 class _KernelLinOp(TwoSidedLinOp, ScaleMixin):
@@ -143,7 +159,7 @@ class _KernelLinOp(TwoSidedLinOp, ScaleMixin):
             return memo[2]
         Pr = ops.pack_points(self._A1, self._kernel_config.lengthscale, blk, layout)
         if kind == "row":
-            packs = (Pr, self._cache.get(layout)[1])
+            packs = (Pr, self._cache.cols(layout))
         else:
             Pc = Pr if self._cache.shared else ops.pack_points(self._A2, self._kernel_config.lengthscale, blk, layout)
             packs = (Pr, Pc)

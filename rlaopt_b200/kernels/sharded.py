@@ -12,12 +12,87 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
+from rlaopt_b200 import ops
+from rlaopt_b200.linops import LinOp
 from rlaopt_b200.linops.spmd import RowShardedLinOp, shard_rows
 
 from .base import _KernelLinOp
 from .configs import KernelConfig
 
-__all__ = ["sharded_kernel_linop", "replicate_from_host"]
+__all__ = ["sharded_kernel_linop", "replicate_from_host", "ShardedKernelLinOp"]
+
+
+class ShardedKernelLinOp(RowShardedLinOp):
+    """Row-sharded kernel operator with the oracles SAP / ASkotch needs, distributed as the reference does it
+    (``rlaopt/kernels/base.py:408-505``):
+
+    * ``row_oracle(blk)``  -- COLUMN mode: every rank owns a chunk of the columns ``A2[lo:hi]``, multiplies
+      ``c K(A1[blk], A2[lo:hi])`` with its rows of ``x`` and the partial results are summed (all-reduce of b x k);
+    * ``blk_oracle(blk)``  -- ROW mode over ``torch.chunk(blk, world)``: every rank computes its rows of
+      ``c K(A1[blk], A2[blk]) @ x`` and the row blocks are all-gathered.
+
+    ``A1`` and ``A2`` are replicated on every rank (one copy per GPU, as ``base.py:143-144``); inputs and outputs of
+    all products are replicated tensors.
+    """
+
+    def __init__(self, A1_dev, A2_dev, kernel_config, kernel, device, group=None):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n, m = A1_dev.shape[0], A2_dev.shape[0]
+        lo, hi = shard_rows(n, world)[rank]
+        self._kernel = kernel.lower()
+        self._cfg = kernel_config.to(device)
+        self._A1, self._A2 = A1_dev, A2_dev
+        local = None
+        if hi > lo:
+            local = _KernelLinOp(A1_dev[lo:hi], A2_dev, self._cfg, _kernel_key=self._kernel)
+        super().__init__(local, torch.Size((n, m)), device, A1_dev.dtype, group)
+        # column chunk of A2 owned by this rank (row oracle) -- its pack is built once, on first use
+        self._clo, self._chi = shard_rows(m, world)[rank]
+        self._col_op = None
+        if self._chi > self._clo:
+            self._col_op = _KernelLinOp(A1_dev, A2_dev[self._clo:self._chi], self._cfg, _kernel_key=self._kernel)
+
+    A1 = property(lambda self: self._A1)
+    A2 = property(lambda self: self._A2)
+    kernel_config = property(lambda self: self._cfg)
+
+    def row_oracle(self, blk: torch.Tensor) -> LinOp:
+        blk_dev = blk.to(self.device)
+        local = self._col_op.row_oracle(blk_dev) if self._col_op is not None else None
+        clo, chi, group = self._clo, self._chi, self.group
+
+        def matmat(x: torch.Tensor) -> torch.Tensor:
+            if local is None:
+                part = x.new_zeros((blk_dev.shape[0],) + tuple(x.shape[1:]))
+            else:
+                part = (local @ x[clo:chi]).contiguous()
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+            return part
+
+        return LinOp(self.device, torch.Size((blk_dev.shape[0], self.shape[1])), matmat, matmat, dtype=self.dtype)
+
+    def blk_oracle(self, blk: torch.Tensor) -> LinOp:
+        blk_dev = blk.to(self.device)
+        b = blk_dev.shape[0]
+        lo, hi = shard_rows(b, self.world)[self.rank]
+        mine = blk_dev[lo:hi]
+        block = -(-b // self.world)
+        cfg, kernel, A1, A2, group, world = self._cfg, self._kernel, self._A1, self._A2, self.group, self.world
+
+        def matmat(x: torch.Tensor) -> torch.Tensor:
+            vec = x.ndim == 1
+            xm = x.unsqueeze(1) if vec else x
+            buf = xm.new_zeros((world * block, xm.shape[1]))
+            if hi > lo:
+                buf[self.rank * block:self.rank * block + (hi - lo)] = ops.kernel_matmat(
+                    A1, A2, xm, kernel, cfg.lengthscale, cfg.const_scaling, row_idx=mine, col_idx=blk_dev)
+            dist.all_gather_into_tensor(buf, buf[self.rank * block:(self.rank + 1) * block], group=group)
+            if world * block != b:  # ragged: drop the padding rows of every rank's slot
+                ranges = shard_rows(b, world)
+                buf = torch.cat([buf[r * block:r * block + (h - l)] for r, (l, h) in enumerate(ranges)])
+            return buf[:, 0] if vec else buf
+
+        return LinOp(self.device, torch.Size((b, b)), matmat, matmat, dtype=self.dtype)
 
 
 def replicate_from_host(T_host: torch.Tensor, device: torch.device,
@@ -46,15 +121,9 @@ def sharded_kernel_linop(
     kernel: str,
     device: torch.device,
     group: Optional[dist.ProcessGroup] = None,
-) -> RowShardedLinOp:
-    """Row-sharded ``c * K(A1, A2)`` for kernel name ``kernel`` ("rbf", "laplace", "matern12|32|52")."""
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    n, m = A1.shape[0], A2.shape[0]
-    lo, hi = shard_rows(n, world)[rank]
+) -> ShardedKernelLinOp:
+    """Row-sharded ``c * K(A1, A2)`` (with SPMD row / block oracles) for kernel name ``kernel`` ("rbf", "laplace", "matern12|32|52")."""
     same = A1 is A2 or (A1.data_ptr() == A2.data_ptr() and A1.shape == A2.shape and A1.device == A2.device)
     A2_dev = A2.to(device)
-    local = None
-    if hi > lo:
-        A1_dev = A2_dev[lo:hi] if same else A1[lo:hi].to(device)
-        local = _KernelLinOp(A1_dev, A2_dev, kernel_config.to(device), _kernel_key=kernel.lower())
-    return RowShardedLinOp(local, torch.Size((n, m)), device, A1.dtype, group)
+    A1_dev = A2_dev if same else A1.to(device)
+    return ShardedKernelLinOp(A1_dev, A2_dev, kernel_config, kernel, device, group)

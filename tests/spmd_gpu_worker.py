@@ -41,6 +41,17 @@ def main():
         if cls is not None:  # bitwise equal to the single-GPU operator on the same rows
             single = cls(Xd, Xd, cfg) @ V.to(dev)
             ok &= bool(torch.allclose(Y, single, rtol=1e-6, atol=1e-6))
+    # SPMD oracles: row oracle = column-sharded partial products + all-reduce, block oracle = row-sharded + all-gather
+    A_sh = sharded_kernel_linop(Xd, Xd, cfg, "rbf", dev)
+    A_one = RBFLinOp(Xd, Xd, cfg)
+    gb = torch.Generator().manual_seed(3)
+    for b in (1, 7, 301, 1000):
+        blk = torch.randperm(n, generator=gb)[:b]
+        Vb = torch.randn(b, k, generator=gb).to(dev)
+        ok &= bool(torch.allclose(A_sh.row_oracle(blk) @ V.to(dev), A_one.row_oracle(blk.to(dev)) @ V.to(dev), rtol=2e-5, atol=2e-5))
+        ok &= bool(torch.allclose(A_sh.blk_oracle(blk) @ Vb, A_one.blk_oracle(blk.to(dev)) @ Vb, rtol=2e-5, atol=2e-5))
+        ok &= bool(torch.allclose(A_sh.blk_oracle(blk) @ Vb[:, 0], A_one.blk_oracle(blk.to(dev)) @ Vb[:, 0], rtol=2e-5, atol=2e-5))
+        ok &= tuple(A_sh.row_oracle(blk).shape) == (b, n) and tuple(A_sh.blk_oracle(blk).shape) == (b, b)
     # replicated-state solvers over the sharded operator; local seeds differ on purpose
     torch.manual_seed(100 + rank)
     A = sharded_kernel_linop(Xd, Xd, KernelConfig(lengthscale=1.0), "rbf", dev)
@@ -49,7 +60,7 @@ def main():
         W, log = LinSys(A, B.to(dev), reg=0.5).solve(
             PCGConfig(device=dev, max_iters=60, rtol=1e-4, precond_config=NystromConfig(rank=80, rho=0.5, sketch="gauss")),
             torch.zeros(n, k, device=dev), callback_freq=1)
-        W2, _ = LinSys(A, B.to(dev), reg=0.5, A_row_oracle=full.row_oracle, A_blk_oracle=full.blk_oracle).solve(
+        W2, _ = LinSys(A, B.to(dev), reg=0.5, A_row_oracle=A.row_oracle, A_blk_oracle=A.blk_oracle).solve(
             SAPConfig(device=dev, max_iters=20, rtol=1e-4, blk_sz=300, precond_config=NystromConfig(rank=40, rho=0.5),
                       accel_config=SAPAccelConfig(mu=0.5, nu=2.0)), torch.zeros(n, k, device=dev), callback_freq=10)
     ok &= bool((log[max(log)]["metrics"]["internal_metrics"]["rel_res"] <= 1e-4).all())
