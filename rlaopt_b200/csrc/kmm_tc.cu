@@ -434,7 +434,7 @@ struct TcParams {
     int64_t n, m;
     int k, kb, nk1, kid;
     int a_stages, v_stages;  // smem ring depths (column-tile images / V images + norms)
-    int nb, la;              // S/P buffers in TMEM, MMA1 look-ahead (tiles)
+    int nb, la;              // S/P buffers in TMEM; la = extra V-ring depth (V of tile t is consumed la tiles after its A image)
     int wide;                // 1: d > 192, feature-chunked MMA1 with X and Y K-blocks streamed through the A ring
     int pair;                // 1: launched as clusters of two CTAs that share every column-tile load (multicast halves)
     int diag;                // RLAOPT_B200_TC_DIAG knock-outs (-DKMM_TC_PROFILE build only): 1 no MMA, 2 no pointwise, 4 no drain, 8 no loads
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     constexpr uint32_t v_norm_off = KP * 256 + 16;
     unsigned char* a_ring = smem;
     unsigned char* v_ring = smem + (size_t)SA * a_stage_bytes;
-    float* xchg = reinterpret_cast<float*>(v_ring + (size_t)SV * v_stage_bytes);  // [2][2][128] row-max exchange
+    float* xchg = reinterpret_cast<float*>(v_ring + (size_t)SV * v_stage_bytes);  // [8][128] per-row tile scales (KP = 128 mode)
     uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 8 * TC_BM);
     uint64_t* a_full = bars;             // [SA] producer -> MMA1
     uint64_t* a_empty = a_full + SA;     // [SA] MMA1 done -> producer
@@ -700,8 +700,8 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     } else {
         // =============================== MMA issue (warps 9, 11: MMA1, warp 10: MMA2) ===============================
         // The whole warp runs the (warp-uniform) control flow so addresses live in uniform
-        // registers; one elected lane issues the tcgen05 instructions.  MMA1 runs LA tiles ahead
-        // of MMA2: with NB >= LA + 2 S/P buffers neither MMA ever waits for the other's completion.
+        // registers; one elected lane issues the tcgen05 instructions.  The MMA1 issuers run ahead of
+        // MMA2 as far as the NB S/P buffers allow, so neither MMA waits for the other's completion.
         constexpr uint32_t idesc1 = umma_idesc(FMT_F16, TC_BN);
         constexpr uint32_t idesc2 = umma_idesc(FMT_F16, KP);
         const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
