@@ -55,6 +55,30 @@ __device__ __forceinline__ void lds_vec(T* dst, const T* src) {
     }
 }
 
+// Packed fp32 pairs (Blackwell FADD2 / FFMA2): one issue slot for two lanes of the FP32 pipe.  The scalar operand of
+// a pair built as {a, a} is encoded as a broadcast source (SASS `R.F32`), so no register copies are spent on it.
+#ifndef KMM_SIMT_PACKED
+#define KMM_SIMT_PACKED 1
+#endif
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void up2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 template <typename T>
 __device__ __forceinline__ T absval(T x);
 template <>
@@ -85,6 +109,7 @@ kmm_simt_kernel(const T* __restrict__ Rt, int64_t n, int64_t n_pad,
     constexpr int NACC = BM * KC / NT;    // phase-2 accumulators per thread
     constexpr int RT = NACC / CT;         // phase-2 rows per thread
     static_assert(RT >= 1 && RT * CT == NACC, "phase-2 tiling must cover the output tile");
+    constexpr bool PACKED = KMM_SIMT_PACKED && sizeof(T) == 4;
 
     const int tid = threadIdx.x;
     const int tx = tid % (BN / TN), ty = tid / (BN / TN);
@@ -176,14 +201,37 @@ kmm_simt_kernel(const T* __restrict__ Rt, int64_t n, int64_t n_pad,
                 alignas(16) T b[TN];
                 lds_vec<T, 8>(a, &sm.As[buf][dd][ty * 8]);
                 lds_vec<T, TN>(b, &sm.Bs[buf][dd][tx * TN]);
+                if constexpr (PACKED) {
+                    // a_r - {b_c, b_c+1} as one FADD2; |.| is a source modifier of the scalar FADD that accumulates
+                    uint64_t bp[TN / 2];
 #pragma unroll
-                for (int r = 0; r < 8; ++r)
+                    for (int c2 = 0; c2 < TN / 2; ++c2) bp[c2] = pk2(b[2 * c2], b[2 * c2 + 1]);
 #pragma unroll
-                    for (int cc = 0; cc < TN; ++cc) {
-                        const T diff = a[r] - b[cc];
-                        if constexpr (L1) S[r][cc] += absval<T>(diff);
-                        else S[r][cc] = fmadd<T>(diff, diff, S[r][cc]);
+                    for (int r = 0; r < 8; ++r) {
+                        const uint64_t ar = pk2(a[r], a[r]);
+#pragma unroll
+                        for (int c2 = 0; c2 < TN / 2; ++c2) {
+                            const uint64_t diff = sub2(ar, bp[c2]);
+                            if constexpr (L1) {
+                                float lo, hi;
+                                up2(diff, lo, hi);
+                                S[r][2 * c2] += fabsf(lo);
+                                S[r][2 * c2 + 1] += fabsf(hi);
+                            } else {
+                                up2(fma2(diff, diff, pk2(S[r][2 * c2], S[r][2 * c2 + 1])), S[r][2 * c2], S[r][2 * c2 + 1]);
+                            }
+                        }
                     }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int cc = 0; cc < TN; ++cc) {
+                            const T diff = a[r] - b[cc];
+                            if constexpr (L1) S[r][cc] += absval<T>(diff);
+                            else S[r][cc] = fmadd<T>(diff, diff, S[r][cc]);
+                        }
+                }
             }
         }
 
@@ -227,10 +275,21 @@ kmm_simt_kernel(const T* __restrict__ Rt, int64_t n, int64_t n_pad,
                 lds_vec<T, RT>(p, &sm.Ps[j][chunk * VEC + (r0 % VEC)]);
             }
             lds_vec<T, CT>(v, &sm.Vs[j][c0]);
+            if constexpr (PACKED) {
 #pragma unroll
-            for (int r = 0; r < RT; ++r)
+                for (int r = 0; r < RT; ++r) {
+                    const uint64_t pr = pk2(p[r], p[r]);
 #pragma unroll
-                for (int c = 0; c < CT; ++c) acc[r][c] = fmadd<T>(p[r], v[c], acc[r][c]);
+                    for (int c2 = 0; c2 < CT / 2; ++c2)
+                        up2(fma2(pr, pk2(v[2 * c2], v[2 * c2 + 1]), pk2(acc[r][2 * c2], acc[r][2 * c2 + 1])),
+                            acc[r][2 * c2], acc[r][2 * c2 + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < RT; ++r)
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) acc[r][c] = fmadd<T>(p[r], v[c], acc[r][c]);
+            }
         }
 
         if (++since_flush == FLUSH_TILES) {
