@@ -409,6 +409,17 @@ __global__ void __launch_bounds__(256) tc_pack_v_kernel(const float* __restrict_
     }
 }
 
+// Register-contraction mode (k <= 4): V[m][k] -> zero-padded fp32 tiles [sub-tile][kv][64], one bulk copy per sub-tile
+__global__ void tc_pack_v_small_kernel(const float* __restrict__ V, int64_t m, int64_t k, int64_t ldv,
+                                       float* __restrict__ tiles, int kv, int64_t sub_tiles) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= sub_tiles * kv * TC_BN) return;
+    const int j = (int)(e % TC_BN);
+    const int c = (int)((e / TC_BN) % kv);
+    const int64_t row = (e / ((int64_t)TC_BN * kv)) * TC_BN + j;
+    tiles[e] = (row < m && c < k) ? V[row * ldv + c] : 0.0f;
+}
+
 // ------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------
@@ -508,8 +519,11 @@ __host__ __device__ constexpr uint32_t tc_v_stage_bytes(int kp) { return (uint32
 // M12: instantiation for Matern-1/2 (carries the near-point recompute; the other kernels stay free of its code)
 // WIDE: d > 192 instantiation (K-block streaming MMA1); kept out of the common kernels, whose C2 throughput drops
 // by 2 % when that code shares their instruction footprint
-template <int KP, int NWG, bool M12, bool WIDE>
+// KV > 0: k <= KV <= 4 columns of V are contracted on the CUDA cores (no MMA2, no P' split, no O buffers): the
+// epilogue thread that owns a row multiplies its 64 kernel values with the raw fp32 V tile from the V ring.
+template <int KP, int NWG, bool M12, bool WIDE, int KV = 0>
 __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcParams p) {
+    static_assert(KV == 0 || (KV <= 4 && KP == 16 && !WIDE), "register contraction: k <= 4, X resident in TMEM");
     constexpr int TC_EPI_WARPS = NWG * 4;
     constexpr int NOB = NWG;  // O buffers: one per epilogue warpgroup (tile u accumulates into O[u % NWG])
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -517,7 +531,8 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     const int KB = p.kb, SA = p.a_stages, SV = p.v_stages, NB = p.nb;
     const uint32_t a_img_bytes = (uint32_t)tc_image_bytes(KB);  // hi + lo image of one 64-point tile in HBM
     const uint32_t a_stage_bytes = WIDE ? TC_WIDE_STAGE_BYTES : a_img_bytes;  // one slot of the A ring
-    constexpr uint32_t v_img_bytes = KP * 256 + 16;             // hi + lo + trailer, as stored in HBM
+    // V tile as stored in HBM: fp16 image hi + lo + trailer, or (KV) the raw fp32 tile [KV][64]
+    constexpr uint32_t v_img_bytes = KV ? KV * 256 : KP * 256 + 16;
     constexpr uint32_t v_stage_bytes = tc_v_stage_bytes(KP);
     constexpr uint32_t v_norm_off = KP * 256 + 16;
     unsigned char* a_ring = smem;
@@ -550,12 +565,12 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         }
         for (int s = 0; s < SV; ++s) {
             mbar_init(&v_full[s], 1);
-            mbar_init(&v_empty[s], consumers);
+            mbar_init(&v_empty[s], KV ? 4 : consumers);  // KV: released by the four warps that read the stage
         }
         for (int b = 0; b < NB; ++b) {
             mbar_init(&s_full[b], 1);
             mbar_init(&p_full[b], 4);  // the four warps of the owning warpgroup
-            mbar_init(&p_free[b], 1);
+            mbar_init(&p_free[b], KV ? 4 : 1);  // KV: S[b] is free once its four warps hold it in registers
         }
         for (int b = 0; b < NOB; ++b) {
             mbar_init(&o_full[b], 1);
@@ -666,6 +681,8 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                     mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
                     bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
                     bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
+                } else if constexpr (KV > 0) {
+                    __trap();  // register-contraction launches are never paired (tc_plan)
                 } else {
                     // each CTA of the pair fetches half of every image and multicasts it to both
                     const uint32_t a_half = a_img_bytes / 2;
@@ -849,7 +866,8 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             if (par == 0) TC_PROF_FLUSH(0)
             }
         } else {
-            // ---- MMA2 issuer ----
+            // ---- MMA2 issuer (idle when the contraction runs on the CUDA cores) ----
+            if constexpr (KV == 0) {
             int b2 = 0, sv = 0;
             uint32_t use2 = 0, phv = 0;
             TC_PROF_DECL
@@ -880,6 +898,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                 }
             }
             TC_PROF_FLUSH(24)
+            }
         }
     }
     } else {
@@ -980,6 +999,11 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         int b = g % NB, sv = g % SV;  // NWG <= NB, SV
         uint32_t use = (uint32_t)((g / NB) & 1), phv = (uint32_t)((g / SV) & 1);
         float dsc_prev = 0.0f;
+        // register-contraction mode: level-1 / level-2 sums per column of V, as (even j, odd j) pairs
+        uint64_t accv[KV ? KV : 1], accv2[KV ? KV : 1];
+#pragma unroll
+        for (int c = 0; c < (KV ? KV : 1); ++c) accv[c] = accv2[c] = 0ull;
+        int lvl = 0;
         TC_PROF_DECL
         for (int u = g; u < T; u += NWG) {
             const unsigned char* vst = v_ring + (size_t)sv * v_stage_bytes;
@@ -995,6 +1019,103 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             tmem_wait_ld();
             TC_PROF(2)
             const float4* nyv = reinterpret_cast<const float4*>(vst + v_norm_off);
+            if constexpr (KV > 0) {
+                // ---- register contraction: Y[row, c] += sum_j f(D_j) V[j, c], c < KV ----
+                tc_fence_before();  // S[b] is in registers: MMA1 may overwrite the buffer
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_free[b]);
+                uint64_t z[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 ny4 = nyv[i];
+                    z[2 * i] = fma2(pack2(__uint_as_float(s0[4 * i]), __uint_as_float(s0[4 * i + 1])), za2,
+                                    fma2(pack2(ny4.x, ny4.y), zc2, zx2));
+                    z[2 * i + 1] = fma2(pack2(__uint_as_float(s0[4 * i + 2]), __uint_as_float(s0[4 * i + 3])), za2,
+                                        fma2(pack2(ny4.z, ny4.w), zc2, zx2));
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 ny4 = nyv[8 + i];
+                    z[16 + 2 * i] = fma2(pack2(__uint_as_float(s1[4 * i]), __uint_as_float(s1[4 * i + 1])), za2,
+                                         fma2(pack2(ny4.x, ny4.y), zc2, zx2));
+                    z[16 + 2 * i + 1] = fma2(pack2(__uint_as_float(s1[4 * i + 2]), __uint_as_float(s1[4 * i + 3])), za2,
+                                             fma2(pack2(ny4.z, ny4.w), zc2, zx2));
+                }
+                if constexpr (M12) {
+                    // near-coincident pairs: same recompute as the tensor-core contraction path below
+                    float ext = 3.0e38f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float z0, z1;
+                        unpack2(z[i], z0, z1);
+                        ext = min3(ext, z0, z1);
+                    }
+                    if (live && ext < 1.0e-3f * nx * nx) {
+                        const int64_t j0 = (t_begin + u) * TC_BN;
+                        const unsigned char* xi = p.rows + tc_image_offset(p.n) + (size_t)(grow >> 6) * a_img_bytes +
+                                                  (size_t)(grow & 63) * 128;
+                        const float* nyf = reinterpret_cast<const float*>(vst + v_norm_off);
+                        float zl[TC_BN];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) unpack2(z[i], zl[2 * i], zl[2 * i + 1]);
+#pragma unroll 1
+                        for (int j = 0; j < TC_BN; ++j) {
+                            const float s2 = nx + nyf[j];
+                            if (zl[j] < 2.25e-4f * s2 * s2 && j0 + j < p.m) {
+                                const int64_t jg = j0 + j;
+                                const unsigned char* yj = col_images + (size_t)(jg >> 6) * a_img_bytes + (size_t)(jg & 63) * 128;
+                                zl[j] = tc_exact_dist2(xi, (int)(grow & 7), yj, (int)(jg & 7), KB, rh->inv_scale, ch->inv_scale);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) z[i] = pack2(zl[2 * i], zl[2 * i + 1]);
+                    }
+                }
+                const float4* v4 = reinterpret_cast<const float4*>(vst);  // raw fp32 V tile, [KV][64]
+                uint64_t ts[KV];  // this tile's sums: (even j, odd j) partial pairs per column of V
+#pragma unroll
+                for (int c = 0; c < KV; ++c) ts[c] = 0ull;
+                const uint64_t nl2 = pack2(-TC_LOG2E, -TC_LOG2E), one2 = pack2(1.0f, 1.0f),
+                               third2 = pack2(1.0f / 3.0f, 1.0f / 3.0f);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    uint64_t pp[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        float z0, z1;
+                        unpack2(z[2 * i + e], z0, z1);
+                        if (is_rbf) {
+                            pp[e] = pack2(ex2_approx(z0), ex2_approx(z1));
+                        } else {
+                            const uint64_t r2 = pack2(sqrt_approx(fmaxf(z0, 0.0f)), sqrt_approx(fmaxf(z1, 0.0f)));
+                            float a0, a1;
+                            unpack2(mul2(r2, nl2), a0, a1);
+                            pp[e] = pack2(ex2_approx(a0), ex2_approx(a1));
+                            if (kid == KID_MATERN32) pp[e] = mul2(pp[e], add2(r2, one2));
+                            else if (kid == KID_MATERN52) pp[e] = mul2(pp[e], fma2(r2, fma2(r2, third2, one2), one2));
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < KV; ++c) {
+                        const float4 vv = v4[c * 16 + i];
+                        ts[c] = fma2(pp[0], pack2(vv.x, vv.y), ts[c]);
+                        ts[c] = fma2(pp[1], pack2(vv.z, vv.w), ts[c]);
+                    }
+                }
+                __syncwarp();  // every lane has read the stage (norms and V)
+                if (lane == 0) mbar_arrive(&v_empty[sv]);
+                // three-level sum: 32 products per partial, one add per tile, one add per 32 tiles
+#pragma unroll
+                for (int c = 0; c < KV; ++c) accv[c] = add2(accv[c], ts[c]);
+                if (++lvl == 32) {
+                    lvl = 0;
+#pragma unroll
+                    for (int c = 0; c < KV; ++c) {
+                        accv2[c] = add2(accv2[c], accv[c]);
+                        accv[c] = 0ull;
+                    }
+                }
+            } else {
             const float vinv = *reinterpret_cast<const float*>(vst + KP * 256);
             if (TC_DIAG(2)) {
                 uint32_t phi[16], plo[16];
@@ -1152,6 +1273,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             TC_PROF(5)
             dsc_prev = dsc;
             }
+            }
             b += NWG;
             if (b >= NB) {
                 b -= NB;
@@ -1165,7 +1287,17 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         }
         if (warp == 0) TC_PROF_FLUSH(8)
         else if (warp == 4) TC_PROF_FLUSH(16)
-        if (SPLIT) {
+        if constexpr (KV > 0) {
+            float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int c = 0; c < KV; ++c) {
+                float lo, hi;
+                unpack2(add2(accv2[c], accv[c]), lo, hi);
+                cs[c] = lo + hi;
+            }
+            acc[0] = pack2(cs[0], cs[1]);
+            acc[1] = pack2(cs[2], cs[3]);
+        } else if (SPLIT) {
             drain_through(T - 1);
         } else {
             const int last = ((T - 1 - g) / NWG) * NWG + g;  // this warpgroup's last tile (T > g)
@@ -1226,7 +1358,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
 }
 
 struct TcPlan {
-    int kb, kp, k_chunks, a_stages, v_stages, nb, la, nwg, wide, splits, tiles_per_split, pair;
+    int kb, kp, k_chunks, a_stages, v_stages, nb, la, nwg, wide, splits, tiles_per_split, pair, kv;
     int64_t sub_tiles;
     size_t smem_bytes, vimg_bytes, part_bytes;
 };
@@ -1248,12 +1380,17 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     // Small d and k: the tensor work per tile is small and the kernel is bound by the pointwise stage (MUFU, TMEM
     // and mbarrier latencies); a third epilogue warpgroup keeps three tiles in flight per SM sub-partition.
     int nwg = (kb <= 2 && kp <= 32 && tc_env_int("RLAOPT_B200_TC_NWG", 3) == 3) ? 3 : 2;
+    // k <= 4 (single right-hand sides: PCG, SAP / ASkotch oracles): the contraction with V runs on the CUDA cores in
+    // the epilogue -- one FFMA2 per two entries and column instead of the fp16 split of P, its TMEM store, MMA2 and
+    // the accumulator drain.  Three epilogue warpgroups, no CTA pairs.  RLAOPT_B200_TC_KV=0 switches it off.
+    int kv = (!wide && k <= 4 && tc_env_int("RLAOPT_B200_TC_KV", 1)) ? (k == 1 ? 1 : (k == 2 ? 2 : 4)) : 0;
+    if (kv) nwg = 3;
     const int x_cols = wide ? 0 : 64 * kb;  // wide d: X streams through smem, only S/P and O live in TMEM
     // TMEM columns: 64 KB (X hi/lo) + 64 NB (S/P) + NWG KP (O) <= 512
     int nb = (512 - x_cols - nwg * kp) / 64;
     if (nb > nwg + 2) nb = nwg + 2;
     if (nb < 2) return false;
-    if (nb < nwg) nwg = 2;
+    if (nb < nwg) nwg = 2, kv = 0;
     if (wide) nb = 4, nwg = 2;  // two-tile segments, double buffered
     if (!wide) nb = max(nwg, min(nb, tc_env_int("RLAOPT_B200_TC_NB", nb)));
     int la = nb >= 4 ? 2 : 1;
@@ -1288,7 +1425,9 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
         const int64_t row_blocks = (n + TC_BM - 1) / TC_BM;
         const int want = tc_env_int("RLAOPT_B200_TC_PAIR", -1);
         pl->pair = row_blocks >= 2 && (want < 0 ? row_blocks >= 2 * (int64_t)sm_count : want != 0);
+        if (kv) pl->pair = 0;
     }
+    pl->kv = kv;
     pl->smem_bytes = sa * a_stage + sv * v_stage + fixed;
     const int64_t base = ((n + TC_BM - 1) / TC_BM) * pl->k_chunks;
     const int64_t target = (int64_t)sm_count * 2;
@@ -1319,7 +1458,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     splits = (pl->sub_tiles + tps - 1) / tps;
     pl->splits = (int)splits;
     pl->tiles_per_split = (int)tps;
-    pl->vimg_bytes = (size_t)pl->k_chunks * pl->sub_tiles * ((size_t)kp * 256 + 16);
+    pl->vimg_bytes = kv ? (size_t)pl->sub_tiles * kv * 256 : (size_t)pl->k_chunks * pl->sub_tiles * ((size_t)kp * 256 + 16);
     pl->part_bytes = splits > 1 ? (size_t)splits * n * k * sizeof(float) : 0;
     return true;
 }
@@ -1360,9 +1499,9 @@ size_t tc_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int sm_cou
     return round_up((int64_t)pl.vimg_bytes, 256) + pl.part_bytes;
 }
 
-template <int KP, int NWG, bool M12, bool WIDE>
+template <int KP, int NWG, bool M12, bool WIDE, int KV = 0>
 static cudaError_t launch_tc_inst(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
-    auto kern = kmm_tc_kernel<KP, NWG, M12, WIDE>;
+    auto kern = kmm_tc_kernel<KP, NWG, M12, WIDE, KV>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (err != cudaSuccess) return err;
     unsigned row_blocks = (unsigned)((n + TC_BM - 1) / TC_BM);
@@ -1402,7 +1541,13 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     if (workspace == nullptr || workspace_bytes < v_bytes + pl.part_bytes) return cudaErrorInvalidValue;
     unsigned char* vimg = static_cast<unsigned char*>(workspace);
     float* part = reinterpret_cast<float*>(vimg + v_bytes);
-    {
+    if (pl.kv) {
+        const int64_t total = pl.sub_tiles * pl.kv * TC_BN;
+        tc_pack_v_small_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(V, m, k, ldv, reinterpret_cast<float*>(vimg),
+                                                                                    pl.kv, pl.sub_tiles);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+    } else {
         const size_t pack_smem = (size_t)TC_BN * (pl.kp + 1) * sizeof(float);
         dim3 grid((unsigned)pl.sub_tiles, (unsigned)pl.k_chunks);
         tc_pack_v_kernel<<<grid, 256, pack_smem, stream>>>(V, m, k, ldv, vimg, pl.kp, pl.sub_tiles);
@@ -1440,6 +1585,14 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
         p.scale_out = scale;
     }
     cudaError_t err;
+    if (pl.kv) {
+        const bool m12 = kid == KID_MATERN12;
+        switch (pl.kv) {
+            case 1: err = m12 ? launch_tc_inst<16, 3, true, false, 1>(p, pl, n, stream) : launch_tc_inst<16, 3, false, false, 1>(p, pl, n, stream); break;
+            case 2: err = m12 ? launch_tc_inst<16, 3, true, false, 2>(p, pl, n, stream) : launch_tc_inst<16, 3, false, false, 2>(p, pl, n, stream); break;
+            default: err = m12 ? launch_tc_inst<16, 3, true, false, 4>(p, pl, n, stream) : launch_tc_inst<16, 3, false, false, 4>(p, pl, n, stream); break;
+        }
+    } else
     switch (pl.kp) {
         case 16: err = pl.nwg == 3 ? launch_tc_kp<16, 3>(p, pl, n, stream) : launch_tc_kp<16, 2>(p, pl, n, stream); break;
         case 32: err = pl.nwg == 3 ? launch_tc_kp<32, 3>(p, pl, n, stream) : launch_tc_kp<32, 2>(p, pl, n, stream); break;
