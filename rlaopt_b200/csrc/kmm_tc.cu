@@ -409,15 +409,21 @@ __global__ void __launch_bounds__(256) tc_pack_v_kernel(const float* __restrict_
     }
 }
 
-// Register-contraction mode (k <= 4): V[m][k] -> zero-padded fp32 tiles [sub-tile][kv][64], one bulk copy per sub-tile
+// Register-contraction mode (k <= 4): V[m][k] and the column norms -> one record per sub-tile,
+// [kv][64] zero-padded fp32 values of V then the 64 squared norms: one bulk copy per sub-tile fills a V-ring stage
 __global__ void tc_pack_v_small_kernel(const float* __restrict__ V, int64_t m, int64_t k, int64_t ldv,
-                                       float* __restrict__ tiles, int kv, int64_t sub_tiles) {
+                                       const float* __restrict__ col_norms, float* __restrict__ tiles, int kv,
+                                       int64_t sub_tiles) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= sub_tiles * kv * TC_BN) return;
+    const int rec = (kv + 1) * TC_BN;
+    if (e >= sub_tiles * rec) return;
     const int j = (int)(e % TC_BN);
-    const int c = (int)((e / TC_BN) % kv);
-    const int64_t row = (e / ((int64_t)TC_BN * kv)) * TC_BN + j;
-    tiles[e] = (row < m && c < k) ? V[row * ldv + c] : 0.0f;
+    const int c = (int)((e / TC_BN) % (kv + 1));
+    const int64_t row = (e / rec) * TC_BN + j;
+    float v;
+    if (c == kv) v = col_norms[row];  // the packed operand holds norms for all padded points
+    else v = (row < m && c < k) ? V[row * ldv + c] : 0.0f;
+    tiles[e] = v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -532,9 +538,9 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     const uint32_t a_img_bytes = (uint32_t)tc_image_bytes(KB);  // hi + lo image of one 64-point tile in HBM
     const uint32_t a_stage_bytes = WIDE ? TC_WIDE_STAGE_BYTES : a_img_bytes;  // one slot of the A ring
     // V tile as stored in HBM: fp16 image hi + lo + trailer, or (KV) the raw fp32 tile [KV][64]
-    constexpr uint32_t v_img_bytes = KV ? KV * 256 : KP * 256 + 16;
+    constexpr uint32_t v_img_bytes = KV ? (KV + 1) * 256 : KP * 256 + 16;  // KV: the record ends with the 64 column norms
     constexpr uint32_t v_stage_bytes = tc_v_stage_bytes(KP);
-    constexpr uint32_t v_norm_off = KP * 256 + 16;
+    constexpr uint32_t v_norm_off = KV ? KV * 256 : KP * 256 + 16;
     unsigned char* a_ring = smem;
     unsigned char* v_ring = smem + (size_t)SA * a_stage_bytes;
     float* xchg = reinterpret_cast<float*>(v_ring + (size_t)SV * v_stage_bytes);  // [8][128] per-row tile scales (KP = 128 mode)
@@ -596,7 +602,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     if (warp >= TC_EPI_WARPS) {
     // registers move from this warpgroup (producer, MMA issue, two idle warps) to the epilogue warpgroups
     if constexpr (NWG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // NWG = 3: 128 at launch; NWG = 4: 96 at launch
     if (warp == TC_EPI_WARPS) {
         // =============================== producer ===============================
         if (lane == 0) {
@@ -673,7 +679,12 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                     mbar_wait(&v_empty[sv], phv);
                     mbar_arrive(&v_full[sv]);
                 } else {
-                if (!p.pair) {
+                if constexpr (KV > 0) {
+                    // the V ring has its own producer (warp TC_EPI_WARPS + 2): at ~700 cycles per sub-tile one thread
+                    // issuing both rings is the bottleneck
+                    mbar_arrive_expect_tx(&a_full[sa], a_img_bytes);
+                    bulk_copy_g2s(a_ring + (size_t)sa * a_img_bytes, a_src, a_img_bytes, &a_full[sa]);
+                } else if (!p.pair) {
                     mbar_arrive_expect_tx(&a_full[sa], a_img_bytes);
                     bulk_copy_g2s(a_ring + (size_t)sa * a_img_bytes, a_src, a_img_bytes, &a_full[sa]);
                     mbar_wait(&v_empty[sv], phv);
@@ -681,8 +692,6 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                     mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
                     bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
                     bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
-                } else if constexpr (KV > 0) {
-                    __trap();  // register-contraction launches are never paired (tc_plan)
                 } else {
                     // each CTA of the pair fetches half of every image and multicasts it to both
                     const uint32_t a_half = a_img_bytes / 2;
@@ -867,7 +876,24 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             }
         } else {
             // ---- MMA2 issuer (idle when the contraction runs on the CUDA cores) ----
-            if constexpr (KV == 0) {
+            if constexpr (KV > 0) {
+                // ---- V-ring producer: one record {V tile, column norms} per sub-tile ----
+                if (lane == 0) {
+                    const unsigned char* v_src = p.vimg + (size_t)t_begin * v_img_bytes;
+                    int sv = 0;
+                    uint32_t phv = 1;
+                    for (int u = 0; u < T; ++u) {
+                        mbar_wait(&v_empty[sv], phv);
+                        mbar_arrive_expect_tx(&v_full[sv], v_img_bytes);
+                        bulk_copy_g2s(v_ring + (size_t)sv * v_stage_bytes, v_src, v_img_bytes, &v_full[sv]);
+                        v_src += v_img_bytes;
+                        if (++sv == SV) {
+                            sv = 0;
+                            phv ^= 1;
+                        }
+                    }
+                }
+            } else {
             int b2 = 0, sv = 0;
             uint32_t use2 = 0, phv = 0;
             TC_PROF_DECL
@@ -903,7 +929,8 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     }
     } else {
         if constexpr (NWG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        else if constexpr (NWG == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");  // 640 threads x 96 = 4 x 32 x 40 + 16 x 32 x 110
         // =============================== epilogue warps ===============================
         const int q = warp & 3;   // TMEM lane quarter this warp may access
         const int h = warp >> 2;  // column half of the sub-tile / of O handled by this warp
@@ -1368,7 +1395,7 @@ int tc_env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* pl) {
+bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* pl, int kid = KID_RBF) {
     if (d < 1 || d > TC_MAX_D_WIDE || n < 1 || m < 1 || k < 1) return false;
     const bool wide = d > TC_MAX_D;
     const int kb = tc_kblocks(d);
@@ -1384,13 +1411,18 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     // the epilogue -- one FFMA2 per two entries and column instead of the fp16 split of P, its TMEM store, MMA2 and
     // the accumulator drain.  Three epilogue warpgroups, no CTA pairs.  RLAOPT_B200_TC_KV=0 switches it off.
     int kv = (!wide && k <= 4 && tc_env_int("RLAOPT_B200_TC_KV", 1)) ? (k == 1 ? 1 : (k == 2 ? 2 : 4)) : 0;
-    if (kv) nwg = 3;
+    // k <= 2 needs few registers per row: a fourth epilogue warpgroup (104 registers per thread) keeps four tiles in
+    // flight per SM sub-partition.  Matern-1/2 (near-pair recompute) and k = 3, 4 stay at three.
+    if (kv) nwg = (kv <= 2 && kid != KID_MATERN12 && tc_env_int("RLAOPT_B200_TC_NWG", 4) == 4) ? 4 : 3;
     const int x_cols = wide ? 0 : 64 * kb;  // wide d: X streams through smem, only S/P and O live in TMEM
     // TMEM columns: 64 KB (X hi/lo) + 64 NB (S/P) + NWG KP (O) <= 512
     int nb = (512 - x_cols - nwg * kp) / 64;
     if (nb > nwg + 2) nb = nwg + 2;
     if (nb < 2) return false;
-    if (nb < nwg) nwg = 2, kv = 0;
+    if (nb < nwg) {
+        if (kv && nwg == 4 && nb >= 3) nwg = 3;
+        else nwg = 2, kv = 0;
+    }
     if (wide) nb = 4, nwg = 2;  // two-tile segments, double buffered
     if (!wide) nb = max(nwg, min(nb, tc_env_int("RLAOPT_B200_TC_NB", nb)));
     int la = nb >= 4 ? 2 : 1;
@@ -1408,7 +1440,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
         sv = sa + la;
     }
     if (sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) return false;
-    if (2 * sa + 2 * sv + 3 * nb + 2 * 3 + 1 > 64) return false;
+    if (2 * sa + 2 * sv + 3 * nb + 2 * 4 + 1 > 64) return false;
     pl->kb = kb;
     pl->kp = kp;
     pl->k_chunks = (int)((k + kp - 1) / kp);
@@ -1458,7 +1490,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     splits = (pl->sub_tiles + tps - 1) / tps;
     pl->splits = (int)splits;
     pl->tiles_per_split = (int)tps;
-    pl->vimg_bytes = kv ? (size_t)pl->sub_tiles * kv * 256 : (size_t)pl->k_chunks * pl->sub_tiles * ((size_t)kp * 256 + 16);
+    pl->vimg_bytes = kv ? (size_t)pl->sub_tiles * (kv + 1) * 256 : (size_t)pl->k_chunks * pl->sub_tiles * ((size_t)kp * 256 + 16);
     pl->part_bytes = splits > 1 ? (size_t)splits * n * k * sizeof(float) : 0;
     return true;
 }
@@ -1536,15 +1568,16 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
                       const float* V, int64_t k, int64_t ldv, float* Y, int64_t ldy, int kid, float scale,
                       int sm_count, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     TcPlan pl;
-    if (!tc_plan(n, m, d, k, sm_count, &pl)) return cudaErrorInvalidValue;
+    if (!tc_plan(n, m, d, k, sm_count, &pl, kid)) return cudaErrorInvalidValue;
     const size_t v_bytes = (size_t)round_up((int64_t)pl.vimg_bytes, 256);
     if (workspace == nullptr || workspace_bytes < v_bytes + pl.part_bytes) return cudaErrorInvalidValue;
     unsigned char* vimg = static_cast<unsigned char*>(workspace);
     float* part = reinterpret_cast<float*>(vimg + v_bytes);
     if (pl.kv) {
-        const int64_t total = pl.sub_tiles * pl.kv * TC_BN;
-        tc_pack_v_small_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(V, m, k, ldv, reinterpret_cast<float*>(vimg),
-                                                                                    pl.kv, pl.sub_tiles);
+        const int64_t total = pl.sub_tiles * (pl.kv + 1) * TC_BN;
+        const float* col_norms = reinterpret_cast<const float*>(static_cast<const unsigned char*>(cols_packed) + tc_norm_offset());
+        tc_pack_v_small_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(V, m, k, ldv, col_norms,
+                                                                                    reinterpret_cast<float*>(vimg), pl.kv, pl.sub_tiles);
         cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) return err;
     } else {
@@ -1588,9 +1621,19 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     if (pl.kv) {
         const bool m12 = kid == KID_MATERN12;
         switch (pl.kv) {
-            case 1: err = m12 ? launch_tc_inst<16, 3, true, false, 1>(p, pl, n, stream) : launch_tc_inst<16, 3, false, false, 1>(p, pl, n, stream); break;
-            case 2: err = m12 ? launch_tc_inst<16, 3, true, false, 2>(p, pl, n, stream) : launch_tc_inst<16, 3, false, false, 2>(p, pl, n, stream); break;
-            default: err = m12 ? launch_tc_inst<16, 3, true, false, 4>(p, pl, n, stream) : launch_tc_inst<16, 3, false, false, 4>(p, pl, n, stream); break;
+            case 1:
+                err = m12 ? launch_tc_inst<16, 3, true, false, 1>(p, pl, n, stream)
+                          : (pl.nwg == 4 ? launch_tc_inst<16, 4, false, false, 1>(p, pl, n, stream)
+                                         : launch_tc_inst<16, 3, false, false, 1>(p, pl, n, stream));
+                break;
+            case 2:
+                err = m12 ? launch_tc_inst<16, 3, true, false, 2>(p, pl, n, stream)
+                          : (pl.nwg == 4 ? launch_tc_inst<16, 4, false, false, 2>(p, pl, n, stream)
+                                         : launch_tc_inst<16, 3, false, false, 2>(p, pl, n, stream));
+                break;
+            default:
+                err = m12 ? launch_tc_inst<16, 3, true, false, 4>(p, pl, n, stream) : launch_tc_inst<16, 3, false, false, 4>(p, pl, n, stream);
+                break;
         }
     } else
     switch (pl.kp) {

@@ -73,8 +73,12 @@ def perf():
         A2 = (torch.randn(m, d, generator=g) / d**0.5).to(dev)
         V = torch.randn(m, k, generator=g).to(dev)
         out = []
-        for kv in ("0", "1"):
-            os.environ["RLAOPT_B200_TC_KV"] = kv
+        variants = [{"RLAOPT_B200_TC_KV": "0"}, {"RLAOPT_B200_TC_KV": "1", "RLAOPT_B200_TC_NWG": "3"},
+                    {"RLAOPT_B200_TC_KV": "1", "RLAOPT_B200_TC_NWG": "4"}]
+        for env in variants:
+            for key in ("RLAOPT_B200_TC_KV", "RLAOPT_B200_TC_NWG"):
+                os.environ.pop(key, None)
+            os.environ.update(env)
             Y = kernel_matmat(A1, A2, V, name, 1.0, layout=LAYOUT_TC)
             torch.cuda.synchronize()
             ts = []
@@ -86,8 +90,10 @@ def perf():
                 torch.cuda.synchronize()
                 ts.append(a.elapsed_time(b))
             out.append(n * m / sorted(ts)[1] / 1e6)
-        print(f"{name:9s} n={n} m={m} d={d} k={k}: MMA2 path {out[0]:7.1f}  register contraction {out[1]:7.1f} Gentries/s "
-              f"({out[1] / out[0]:.2f}x)   (includes packing X and V per call)", flush=True)
+        for key in ("RLAOPT_B200_TC_KV", "RLAOPT_B200_TC_NWG"):
+            os.environ.pop(key, None)
+        print(f"{name:9s} n={n} m={m} d={d} k={k}: MMA2 path {out[0]:7.1f} | register contraction, 3 warpgroups {out[1]:7.1f} "
+              f"| 4 warpgroups {out[2]:7.1f} Gentries/s (includes packing X and V per call)", flush=True)
 
 
 if __name__ == "__main__":
