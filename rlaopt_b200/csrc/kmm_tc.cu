@@ -1430,7 +1430,11 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     // smem: A ring (column-tile images) + V ring (la stages deeper: V of tile t is consumed la tiles after its A)
     const size_t a_stage = wide ? (size_t)TC_WIDE_STAGE_BYTES : tc_image_bytes(kb), v_stage = tc_v_stage_bytes(kp);
     const size_t fixed = 8 * TC_BM * sizeof(float) + 64 * sizeof(uint64_t) + 64;
-    int sa = 4, sv;
+    // ring depth: a 16 KB image is ~2000 cycles in flight; the MMA2 path consumes one per >= 1000 cycles (4 stages),
+    // the register-contraction path one per ~600 (deeper ring, RLAOPT_B200_TC_SA overrides)
+    int sa = tc_env_int("RLAOPT_B200_TC_SA", kv ? 8 : 4), sv;
+    if (sa < 2) sa = 2;
+    if (sa > 10) sa = 10;
     if (wide) {  // V images of one or two segments in flight, the rest of smem for 64 KB K-block slots
         sv = kp > 64 ? 2 : 4;
         sa = 3;

@@ -64,6 +64,32 @@ def acc():
     print("worst", worst, "OK" if worst <= 2e-6 else "FAIL")
 
 
+def sweep():
+    """ring depth / S buffers of the register-contraction mode"""
+    name, n, m, d, k = "rbf", 131072, 1 << 20, 16, 1
+    g = torch.Generator().manual_seed(0)
+    A1 = (torch.randn(n, d, generator=g) / d**0.5).to(dev)
+    A2 = (torch.randn(m, d, generator=g) / d**0.5).to(dev)
+    V = torch.randn(m, k, generator=g).to(dev)
+    for env in [{"RLAOPT_B200_TC_SA": "4"}, {"RLAOPT_B200_TC_SA": "6"}, {"RLAOPT_B200_TC_SA": "8"}, {"RLAOPT_B200_TC_SA": "10"},
+                {"RLAOPT_B200_TC_SA": "8", "RLAOPT_B200_TC_NB": "4"}, {"RLAOPT_B200_TC_SA": "8", "RLAOPT_B200_TC_LA": "1"},
+                {"RLAOPT_B200_TC_SA": "8", "RLAOPT_B200_TC_LA": "4"}, {"RLAOPT_B200_TC_SA": "8", "RLAOPT_B200_TC_NWG": "3"}]:
+        for key in ("RLAOPT_B200_TC_SA", "RLAOPT_B200_TC_NB", "RLAOPT_B200_TC_LA", "RLAOPT_B200_TC_NWG"):
+            os.environ.pop(key, None)
+        os.environ.update(env)
+        Y = kernel_matmat(A1, A2, V, name, 1.0, layout=LAYOUT_TC)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            Y = kernel_matmat(A1, A2, V, name, 1.0, layout=LAYOUT_TC)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        print(f"{env}: {n * m / sorted(ts)[1] / 1e6:7.1f} Gentries/s", flush=True)
+
+
 def perf():
     for name, n, m, d, k in [("rbf", 131072, 1 << 20, 16, 1), ("rbf", 131072, 1 << 20, 8, 1), ("rbf", 131072, 1 << 20, 32, 2),
                              ("rbf", 131072, 1 << 20, 32, 4), ("matern52", 131072, 1 << 20, 16, 1),
@@ -98,4 +124,4 @@ def perf():
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "acc"
-    acc() if what == "acc" else perf()
+    {"acc": acc, "perf": perf, "sweep": sweep}[what]()

@@ -252,3 +252,70 @@ def test_wide_feature_variant(dev, name, n, m, d, k):
     ref_t = ko.kernel_matmat_gemm_form(A2, A1, W, name, 1.1, 0.5, dtype=torch.float64)
     got_t = kernel_matmat(A1.to(dev), A2.to(dev), W.to(dev), name, 1.1, 0.5, transpose=True, layout=LAYOUT_TC)
     assert ko.rel_fro_error(got_t, ref_t) <= 1e-5
+
+
+# ---- register-contraction mode (k <= 4: P.V on the CUDA cores in the epilogue, no MMA2) ----
+@pytest.mark.parametrize("name", TC_KERNELS)
+@pytest.mark.parametrize(
+    "n,m,d,k",
+    [(1, 1, 1, 1), (70, 64, 8, 1), (70, 65, 8, 1), (129, 64 * 3, 16, 2), (300, 64 * 5 + 7, 100, 3), (257, 64 * 33 + 1, 150, 4),
+     (40, 50000, 16, 1), (20000, 300, 32, 1), (1500, 1500, 192, 2)],
+)
+def test_register_contraction_against_fp64_oracle(dev, name, n, m, d, k, monkeypatch):
+    """k = 1 ... 4 with ragged tiles, one to many sub-tiles (three / four epilogue warpgroups alternate over them),
+    the split-column launch (small n, large m), d up to the resident-X limit; the MMA2 path on the same inputs."""
+    from rlaopt_b200._lib import LAYOUT_TC
+    from rlaopt_b200.ops import kernel_matmat
+
+    A1, A2 = _rand((n, d), 41) / d**0.5, _rand((m, d), 42) / d**0.5
+    V, W = _rand((m, k), 43), _rand((n, k), 44)
+    ref = ko.kernel_matmat_gemm_form(A1, A2, V, name, 1.1, 0.7, dtype=torch.float64)
+    ref_t = ko.kernel_matmat_gemm_form(A2, A1, W, name, 1.1, 0.7, dtype=torch.float64)
+    for mode in ("1", "0"):
+        monkeypatch.setenv("RLAOPT_B200_TC_KV", mode)
+        got = kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), name, 1.1, 0.7, layout=LAYOUT_TC)
+        assert got.shape == (n, k)
+        assert ko.rel_fro_error(got, ref) <= (2e-6 if mode == "1" else 1e-5), (name, n, m, d, k, mode)
+        got_t = kernel_matmat(A1.to(dev), A2.to(dev), W.to(dev), name, 1.1, 0.7, transpose=True, layout=LAYOUT_TC)
+        assert ko.rel_fro_error(got_t, ref_t) <= (2e-6 if mode == "1" else 1e-5)
+
+
+def test_register_contraction_vector_operand_gather_and_warpgroup_counts(dev, monkeypatch):
+    """1-D operand, row / column index gathers (the SAP / ASkotch oracles), three and four epilogue warpgroups."""
+    from rlaopt_b200._lib import LAYOUT_TC
+    from rlaopt_b200.ops import kernel_matmat
+
+    n, d = 3000, 16
+    X = _rand((n, d), 45) / d**0.5
+    v = _rand((n,), 46)
+    rows = torch.randperm(n, generator=torch.Generator().manual_seed(47))[:700]
+    cols = torch.randperm(n, generator=torch.Generator().manual_seed(48))[:1100]
+    ref = ko.kernel_matmat_gemm_form(X[rows], X[cols], v[cols, None], "rbf", 1.0, dtype=torch.float64)[:, 0]
+    outs = []
+    for nwg in ("4", "3"):
+        monkeypatch.setenv("RLAOPT_B200_TC_NWG", nwg)
+        got = kernel_matmat(X.to(dev), X.to(dev), v[cols].to(dev), "rbf", 1.0, row_idx=rows.to(dev), col_idx=cols.to(dev),
+                            layout=LAYOUT_TC)
+        assert got.shape == (700,)
+        assert ko.rel_fro_error(got, ref) <= 2e-6, nwg
+        outs.append(got)
+    # the warpgroups own different sub-tiles in the two runs: equal up to the order of the partial sums
+    assert ko.rel_fro_error(outs[0], outs[1].double().cpu()) <= 1e-6
+
+
+def test_register_contraction_long_positive_sum_and_tiny_values(dev):
+    """Three-level summation over 6000 sub-tiles of positive terms; rows whose kernel values are all ~1e-30 keep
+    fp32 relative accuracy (no fp16 range involved on this path)."""
+    from rlaopt_b200._lib import LAYOUT_TC
+    from rlaopt_b200.ops import kernel_matmat
+
+    g = torch.Generator().manual_seed(49)
+    A1, A2 = _rand((300, 8), 50) / 8**0.5, _rand((384000, 8), 51) / 8**0.5
+    V = torch.rand(384000, 1, generator=g)
+    ref = ko.kernel_matmat_gemm_form(A1, A2, V, "rbf", 1.0, dtype=torch.float64)
+    got = kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), "rbf", 1.0, layout=LAYOUT_TC)
+    assert ko.rel_fro_error(got, ref) <= 1e-6
+    far = A1 + 4.2  # squared distances ~ 140: K ~ 1e-30
+    ref = ko.kernel_matmat_gemm_form(far, A2[:5000], V[:5000], "rbf", 1.0, dtype=torch.float64)
+    got = kernel_matmat(far.to(dev), A2[:5000].to(dev), V[:5000].to(dev), "rbf", 1.0, layout=LAYOUT_TC)
+    assert ko.rel_fro_error(got, ref) <= 2e-4  # eps (|x|^2 + |y|^2) of the GEMM-form distance times log-slope; values ~1e-30
