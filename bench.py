@@ -244,6 +244,33 @@ def krr_pcg_solve(device, linop_factory, reps: int = 1) -> dict:
             "config": "RBF KRR n=20000 d=8 k=1, Nystrom rank 200 (gauss), reg=1.0, rtol=1e-4, fp32, callback_freq=1"}
 
 
+def single_rhs_matvec(device) -> dict:
+    """Row-oracle shaped product with one right-hand side (the SAP / ASkotch and single-RHS PCG hot path, BASELINE
+    configs[3] per-step shape scaled to one GPU): K(X[:b], X) @ v, RBF, n = 2M, b = 65536, d = 16, k = 1, fp32."""
+    from rlaopt_b200.kernels import KernelConfig, RBFLinOp
+
+    n, b, d = 2_000_000, 65_536, 16
+    g = torch.Generator().manual_seed(0)
+    X = (torch.randn(n, d, generator=g) / d**0.5).to(device)
+    v = torch.randn(n, generator=g).to(device)
+    op = RBFLinOp(X[:b].contiguous(), X, KernelConfig(lengthscale=1.0))
+    for _ in range(2):
+        y = op @ v
+    torch.cuda.synchronize(device)
+    ts = []
+    for _ in range(5):
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        y = op @ v
+        e.record()
+        torch.cuda.synchronize(device)
+        ts.append(a.elapsed_time(e))
+    ms = sorted(ts)[len(ts) // 2]
+    return {"value": b * n / ms / 1e6, "unit": "Gentries/s", "ms": ms,
+            "config": f"RBF K(X[:{b}], X) @ v, n={n}, d={d}, k=1, fp32 (V re-packed per call, X packs cached)",
+            "checksum_abs_sum": float(y.double().abs().sum().item())}
+
+
 # ----------------------------------------------------------------------------- ours
 def run_ours(args) -> int:
     import torch.distributed as dist
@@ -421,6 +448,7 @@ def run_ours(args) -> int:
         del op, Y, Vg
         torch.cuda.empty_cache()
         line["krr_pcg"] = krr_pcg_solve(dev, lambda Xd: RBFLinOp(Xd, Xd, cfg), reps=2)
+        line["single_rhs_matvec"] = single_rhs_matvec(dev)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

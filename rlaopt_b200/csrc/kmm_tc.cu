@@ -976,6 +976,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         // are added at the end.  KP = 128 (k > 64): both warpgroups drain every tile, half of the columns each,
         // so a thread still carries 64 accumulators; the owner publishes the tile's scale through smem.
         constexpr bool SPLIT = KP > 64;
+        constexpr bool FRAG = KV > 0 && !M12;
         constexpr int DW = SPLIT ? KP / 2 : KP;  // O columns one thread accumulates
         uint64_t acc[DW / 2];                    // fp32 pairs
 #pragma unroll
@@ -1031,6 +1032,22 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
 #pragma unroll
         for (int c = 0; c < (KV ? KV : 1); ++c) accv[c] = accv2[c] = 0ull;
         int lvl = 0;
+        // FRAG (register contraction, all kernels but Matern-1/2): S is read in the 16x256b fragment pattern, so a
+        // thread holds 4 rows x 16 columns of the sub-tile instead of 1 row x 64 columns and loads the norms and V
+        // values of 16 columns only -- with one row per thread the broadcast loads (512 B per thread and sub-tile)
+        // kept the shared-memory pipe 79 % busy and bounded the kernel.  Row r = 2 hf + s of a thread is TMEM lane
+        // 32 q + lane / 4 + 8 s + 16 hf; its columns are 8 i + 2 (lane % 4) + {0, 1}, i = 0..7.
+        const int tq = lane & 3;
+        uint64_t zxr2[4];
+        float accf[4][KV ? KV : 1], accf2[4][KV ? KV : 1];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int64_t gr = row0 + q * 32 + (lane >> 2) + 8 * (r & 1) + 16 * (r >> 1);
+            const float nxr = (FRAG && gr < tc_npad(p.n)) ? reinterpret_cast<const float*>(p.rows + tc_norm_offset())[gr] : 0.0f;
+            zxr2[r] = pack2(nxr * zc, nxr * zc);
+#pragma unroll
+            for (int c = 0; c < (KV ? KV : 1); ++c) accf[r][c] = accf2[r][c] = 0.0f;
+        }
         TC_PROF_DECL
         for (int u = g; u < T; u += NWG) {
             const unsigned char* vst = v_ring + (size_t)sv * v_stage_bytes;
@@ -1041,12 +1058,84 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             tc_fence_after();
             const uint32_t t_s = tmem + lane_bits + col_sp + b * 64;
             uint32_t s0[32], s1[32];
-            tmem_ld32(t_s, s0);
-            tmem_ld32(t_s + 32, s1);
+            if constexpr (FRAG) {
+                tmem_ld_16x256b_x8(t_s, s0);                // lanes 32q + [0, 16)
+                tmem_ld_16x256b_x8(t_s + (16u << 16), s1);  // lanes 32q + [16, 32)
+            } else {
+                tmem_ld32(t_s, s0);
+                tmem_ld32(t_s + 32, s1);
+            }
             tmem_wait_ld();
             TC_PROF(2)
             const float4* nyv = reinterpret_cast<const float4*>(vst + v_norm_off);
-            if constexpr (KV > 0) {
+            if constexpr (FRAG) {
+                // ---- register contraction, fragment layout: 4 rows x 16 columns per thread ----
+                tc_fence_before();  // S[b] is in registers: MMA1 may overwrite the buffer
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_free[b]);
+                const float2* ny2 = reinterpret_cast<const float2*>(vst + v_norm_off);
+                const float2* v2 = reinterpret_cast<const float2*>(vst);  // raw fp32 V tile, [KV][64]
+                uint64_t ts[4][KV];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < KV; ++c) ts[r][c] = 0ull;
+                const uint64_t nl2 = pack2(-TC_LOG2E, -TC_LOG2E), one2 = pack2(1.0f, 1.0f),
+                               third2 = pack2(1.0f / 3.0f, 1.0f / 3.0f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 nyp = ny2[4 * i + tq];
+                    const uint64_t nyc = mul2(pack2(nyp.x, nyp.y), zc2);
+                    uint64_t vp[KV];
+#pragma unroll
+                    for (int c = 0; c < KV; ++c) {
+                        const float2 vv = v2[c * 32 + 4 * i + tq];
+                        vp[c] = pack2(vv.x, vv.y);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int o = 4 * i + 2 * (r & 1);
+                        const uint64_t sp = (r < 2) ? pack2(__uint_as_float(s0[o]), __uint_as_float(s0[o + 1]))
+                                                    : pack2(__uint_as_float(s1[o]), __uint_as_float(s1[o + 1]));
+                        float z0, z1;
+                        unpack2(fma2(sp, za2, add2(nyc, zxr2[r])), z0, z1);
+                        uint64_t pp;
+                        if (is_rbf) {
+                            pp = pack2(ex2_approx(z0), ex2_approx(z1));
+                        } else {
+                            const uint64_t r2 = pack2(sqrt_approx(fmaxf(z0, 0.0f)), sqrt_approx(fmaxf(z1, 0.0f)));
+                            float a0, a1;
+                            unpack2(mul2(r2, nl2), a0, a1);
+                            pp = pack2(ex2_approx(a0), ex2_approx(a1));
+                            if (kid == KID_MATERN32) pp = mul2(pp, add2(r2, one2));
+                            else if (kid == KID_MATERN52) pp = mul2(pp, fma2(r2, fma2(r2, third2, one2), one2));
+                        }
+#pragma unroll
+                        for (int c = 0; c < KV; ++c) ts[r][c] = fma2(pp, vp[c], ts[r][c]);
+                    }
+                }
+                __syncwarp();  // every lane has read the stage (norms and V)
+                if (lane == 0) mbar_arrive(&v_empty[sv]);
+                // three-level sum: 8 products per partial, one add per tile, one add per 32 tiles
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < KV; ++c) {
+                        float lo, hi;
+                        unpack2(ts[r][c], lo, hi);
+                        accf[r][c] += lo + hi;
+                    }
+                if (++lvl == 32) {
+                    lvl = 0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < KV; ++c) {
+                            accf2[r][c] += accf[r][c];
+                            accf[r][c] = 0.0f;
+                        }
+                }
+            } else if constexpr (KV > 0) {
                 // ---- register contraction: Y[row, c] += sum_j f(D_j) V[j, c], c < KV ----
                 tc_fence_before();  // S[b] is in registers: MMA1 may overwrite the buffer
                 __syncwarp();
@@ -1314,6 +1403,40 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         }
         if (warp == 0) TC_PROF_FLUSH(8)
         else if (warp == 4) TC_PROF_FLUSH(16)
+        if constexpr (FRAG) {
+            // row sums: the four lanes that share a row hold the partial sums of their column subsets
+            float rs[4][KV];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < KV; ++c) {
+                    float v = accf2[r][c] + accf[r][c];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    rs[r][c] = v;
+                }
+            float* ysm = reinterpret_cast<float*>(smem);  // [NWG][128][KV], reuses the A ring
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");  // every warpgroup is done with the rings
+            if (tq == 0) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int rl = q * 32 + (lane >> 2) + 8 * (r & 1) + 16 * (r >> 1);
+#pragma unroll
+                    for (int c = 0; c < KV; ++c) ysm[(g * TC_BM + rl) * KV + c] = rs[r][c];
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+            if (g == 0 && grow < p.n) {
+                float* dst = p.out + (int64_t)blockIdx.z * p.split_stride + grow * p.ldo;
+#pragma unroll
+                for (int c = 0; c < KV; ++c) {
+                    float y = 0.0f;
+#pragma unroll
+                    for (int w = 0; w < NWG; ++w) y += ysm[(w * TC_BM + row) * KV + c];
+                    if (c < p.k) dst[c] = y * p.scale_out;
+                }
+            }
+        } else {
         if constexpr (KV > 0) {
             float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
@@ -1376,6 +1499,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                 }
             }
         }
+        }
     }
 
     tc_fence_before();
@@ -1411,9 +1535,9 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     // the epilogue -- one FFMA2 per two entries and column instead of the fp16 split of P, its TMEM store, MMA2 and
     // the accumulator drain.  Three epilogue warpgroups, no CTA pairs.  RLAOPT_B200_TC_KV=0 switches it off.
     int kv = (!wide && k <= 4 && tc_env_int("RLAOPT_B200_TC_KV", 1)) ? (k == 1 ? 1 : (k == 2 ? 2 : 4)) : 0;
-    // k <= 2 needs few registers per row: a fourth epilogue warpgroup (104 registers per thread) keeps four tiles in
-    // flight per SM sub-partition.  Matern-1/2 (near-pair recompute) and k = 3, 4 stay at three.
-    if (kv) nwg = (kv <= 2 && kid != KID_MATERN12 && tc_env_int("RLAOPT_B200_TC_NWG", 4) == 4) ? 4 : 3;
+    // k = 1 needs few registers: a fourth epilogue warpgroup (104 registers per thread) keeps four tiles in flight
+    // per SM sub-partition.  Matern-1/2 (near-pair recompute) and k = 2 ... 4 stay at three.
+    if (kv) nwg = (kv == 1 && kid != KID_MATERN12 && tc_env_int("RLAOPT_B200_TC_NWG", 4) == 4) ? 4 : 3;
     const int x_cols = wide ? 0 : 64 * kb;  // wide d: X streams through smem, only S/P and O live in TMEM
     // TMEM columns: 64 KB (X hi/lo) + 64 NB (S/P) + NWG KP (O) <= 512
     int nb = (512 - x_cols - nwg * kp) / 64;
@@ -1430,11 +1554,10 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     // smem: A ring (column-tile images) + V ring (la stages deeper: V of tile t is consumed la tiles after its A)
     const size_t a_stage = wide ? (size_t)TC_WIDE_STAGE_BYTES : tc_image_bytes(kb), v_stage = tc_v_stage_bytes(kp);
     const size_t fixed = 8 * TC_BM * sizeof(float) + 64 * sizeof(uint64_t) + 64;
-    // ring depth: a 16 KB image is ~2000 cycles in flight; the MMA2 path consumes one per >= 1000 cycles (4 stages),
-    // the register-contraction path one per ~600 (deeper ring, RLAOPT_B200_TC_SA overrides)
-    int sa = tc_env_int("RLAOPT_B200_TC_SA", kv ? 8 : 4), sv;
+    // ring depth: 4 stages; deeper rings measured no gain even at one sub-tile per ~600 cycles (RLAOPT_B200_TC_SA)
+    int sa = tc_env_int("RLAOPT_B200_TC_SA", 4), sv;
     if (sa < 2) sa = 2;
-    if (sa > 10) sa = 10;
+    if (sa > 8) sa = 8;
     if (wide) {  // V images of one or two segments in flight, the rest of smem for 64 KB K-block slots
         sv = kp > 64 ? 2 : 4;
         sa = 3;
@@ -1631,9 +1754,7 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
                                          : launch_tc_inst<16, 3, false, false, 1>(p, pl, n, stream));
                 break;
             case 2:
-                err = m12 ? launch_tc_inst<16, 3, true, false, 2>(p, pl, n, stream)
-                          : (pl.nwg == 4 ? launch_tc_inst<16, 4, false, false, 2>(p, pl, n, stream)
-                                         : launch_tc_inst<16, 3, false, false, 2>(p, pl, n, stream));
+                err = m12 ? launch_tc_inst<16, 3, true, false, 2>(p, pl, n, stream) : launch_tc_inst<16, 3, false, false, 2>(p, pl, n, stream);
                 break;
             default:
                 err = m12 ? launch_tc_inst<16, 3, true, false, 4>(p, pl, n, stream) : launch_tc_inst<16, 3, false, false, 4>(p, pl, n, stream);
