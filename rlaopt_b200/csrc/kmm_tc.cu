@@ -527,7 +527,9 @@ __host__ __device__ constexpr uint32_t tc_v_stage_bytes(int kp) { return (uint32
 // by 2 % when that code shares their instruction footprint
 // KV > 0: k <= KV <= 4 columns of V are contracted on the CUDA cores (no MMA2, no P' split, no O buffers): the
 // epilogue thread that owns a row multiplies its 64 kernel values with the raw fp32 V tile from the V ring.
-template <int KP, int NWG, bool M12, bool WIDE, int KV = 0>
+// KIDT >= 0: kernel id fixed at compile time (register-contraction instantiations: the fully unrolled epilogue is
+// sensitive to its instruction footprint, so it carries the code of one kernel function only)
+template <int KP, int NWG, bool M12, bool WIDE, int KV = 0, int KIDT = -1>
 __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcParams p) {
     static_assert(KV == 0 || (KV <= 4 && KP == 16 && !WIDE), "register contraction: k <= 4, X resident in TMEM");
     constexpr int TC_EPI_WARPS = NWG * 4;
@@ -602,7 +604,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     if (warp >= TC_EPI_WARPS) {
     // registers move from this warpgroup (producer, MMA issue, two idle warps) to the epilogue warpgroups
     if constexpr (NWG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // NWG = 3: 128 at launch; NWG = 4: 96 at launch
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == TC_EPI_WARPS) {
         // =============================== producer ===============================
         if (lane == 0) {
@@ -929,8 +931,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     }
     } else {
         if constexpr (NWG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-        else if constexpr (NWG == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");  // 640 threads x 96 = 4 x 32 x 40 + 16 x 32 x 110
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         // =============================== epilogue warps ===============================
         const int q = warp & 3;   // TMEM lane quarter this warp may access
         const int h = warp >> 2;  // column half of the sub-tile / of O handled by this warp
@@ -1015,14 +1016,14 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         };
 
         // per-kernel constants of pass 1: z = S * za + (|y|^2 * zc + zx)
+        const int kid = KIDT >= 0 ? KIDT : p.kid;
         float zc;
-        if (p.kid == KID_RBF) zc = -0.5f * TC_LOG2E;
-        else if (p.kid == KID_MATERN32) zc = 3.0f;
-        else if (p.kid == KID_MATERN52) zc = 5.0f;
+        if (kid == KID_RBF) zc = -0.5f * TC_LOG2E;
+        else if (kid == KID_MATERN32) zc = 3.0f;
+        else if (kid == KID_MATERN52) zc = 5.0f;
         else zc = 1.0f;
         const uint64_t za2 = pack2(m2c * zc, m2c * zc), zc2 = pack2(zc, zc), zx2 = pack2(nx * zc, nx * zc);
-        const bool is_rbf = p.kid == KID_RBF;
-        const int kid = p.kid;
+        const bool is_rbf = kid == KID_RBF;
 
         int b = g % NB, sv = g % SV;  // NWG <= NB, SV
         uint32_t use = (uint32_t)((g / NB) & 1), phv = (uint32_t)((g / SV) & 1);
@@ -1519,7 +1520,7 @@ int tc_env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* pl, int kid = KID_RBF) {
+bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* pl) {
     if (d < 1 || d > TC_MAX_D_WIDE || n < 1 || m < 1 || k < 1) return false;
     const bool wide = d > TC_MAX_D;
     const int kb = tc_kblocks(d);
@@ -1535,18 +1536,13 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     // the epilogue -- one FFMA2 per two entries and column instead of the fp16 split of P, its TMEM store, MMA2 and
     // the accumulator drain.  Three epilogue warpgroups, no CTA pairs.  RLAOPT_B200_TC_KV=0 switches it off.
     int kv = (!wide && k <= 4 && tc_env_int("RLAOPT_B200_TC_KV", 1)) ? (k == 1 ? 1 : (k == 2 ? 2 : 4)) : 0;
-    // k = 1 needs few registers: a fourth epilogue warpgroup (104 registers per thread) keeps four tiles in flight
-    // per SM sub-partition.  Matern-1/2 (near-pair recompute) and k = 2 ... 4 stay at three.
-    if (kv) nwg = (kv == 1 && kid != KID_MATERN12 && tc_env_int("RLAOPT_B200_TC_NWG", 4) == 4) ? 4 : 3;
+    if (kv) nwg = 3;  // a fourth epilogue warpgroup (640 threads, 104 registers) measured 3 % slower at k = 1
     const int x_cols = wide ? 0 : 64 * kb;  // wide d: X streams through smem, only S/P and O live in TMEM
     // TMEM columns: 64 KB (X hi/lo) + 64 NB (S/P) + NWG KP (O) <= 512
     int nb = (512 - x_cols - nwg * kp) / 64;
     if (nb > nwg + 2) nb = nwg + 2;
     if (nb < 2) return false;
-    if (nb < nwg) {
-        if (kv && nwg == 4 && nb >= 3) nwg = 3;
-        else nwg = 2, kv = 0;
-    }
+    if (nb < nwg) nwg = 2, kv = 0;
     if (wide) nb = 4, nwg = 2;  // two-tile segments, double buffered
     if (!wide) nb = max(nwg, min(nb, tc_env_int("RLAOPT_B200_TC_NB", nb)));
     int la = nb >= 4 ? 2 : 1;
@@ -1567,7 +1563,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
         sv = sa + la;
     }
     if (sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) return false;
-    if (2 * sa + 2 * sv + 3 * nb + 2 * 4 + 1 > 64) return false;
+    if (2 * sa + 2 * sv + 3 * nb + 2 * 3 + 1 > 64) return false;
     pl->kb = kb;
     pl->kp = kp;
     pl->k_chunks = (int)((k + kp - 1) / kp);
@@ -1658,9 +1654,9 @@ size_t tc_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int sm_cou
     return round_up((int64_t)pl.vimg_bytes, 256) + pl.part_bytes;
 }
 
-template <int KP, int NWG, bool M12, bool WIDE, int KV = 0>
+template <int KP, int NWG, bool M12, bool WIDE, int KV = 0, int KIDT = -1>
 static cudaError_t launch_tc_inst(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
-    auto kern = kmm_tc_kernel<KP, NWG, M12, WIDE, KV>;
+    auto kern = kmm_tc_kernel<KP, NWG, M12, WIDE, KV, KIDT>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (err != cudaSuccess) return err;
     unsigned row_blocks = (unsigned)((n + TC_BM - 1) / TC_BM);
@@ -1687,15 +1683,46 @@ static cudaError_t launch_tc_kp(const TcParams& p, const TcPlan& pl, int64_t n, 
             return p.kid == KID_MATERN12 ? launch_tc_inst<KP, NWG, true, true>(p, pl, n, stream)
                                          : launch_tc_inst<KP, NWG, false, true>(p, pl, n, stream);
     }
-    return p.kid == KID_MATERN12 ? launch_tc_inst<KP, NWG, true, false>(p, pl, n, stream)
-                                 : launch_tc_inst<KP, NWG, false, false>(p, pl, n, stream);
+    {
+        // X-resident families: one kernel function per instantiation, see KIDT (Matern-1/2, -3/2, -5/2 at d = 32,
+        // k = 16: +21 %, +19 %, +10 %; RBF +3.5 %)
+        switch (p.kid) {
+            case KID_RBF: return launch_tc_inst<KP, NWG, false, false, 0, KID_RBF>(p, pl, n, stream);
+            case KID_MATERN32: return launch_tc_inst<KP, NWG, false, false, 0, KID_MATERN32>(p, pl, n, stream);
+            case KID_MATERN52: return launch_tc_inst<KP, NWG, false, false, 0, KID_MATERN52>(p, pl, n, stream);
+            default: return launch_tc_inst<KP, NWG, true, false, 0, KID_MATERN12>(p, pl, n, stream);
+        }
+    }
+}
+
+// register-contraction instantiations: (k <= 1, 2, 4) x (RBF, Matern-3/2, Matern-5/2 fixed at compile time; Matern-1/2
+// with its near-pair recompute), three epilogue warpgroups
+template <int KV, int KIDT>
+static cudaError_t launch_tc_kv_kid(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
+    return launch_tc_inst<16, 3, false, false, KV, KIDT>(p, pl, n, stream);
+}
+template <int KV>
+static cudaError_t launch_tc_kv_k(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
+    switch (p.kid) {
+        case KID_RBF: return launch_tc_kv_kid<KV, KID_RBF>(p, pl, n, stream);
+        case KID_MATERN32: return launch_tc_kv_kid<KV, KID_MATERN32>(p, pl, n, stream);
+        case KID_MATERN52: return launch_tc_kv_kid<KV, KID_MATERN52>(p, pl, n, stream);
+        default: return launch_tc_inst<16, 3, true, false, KV, KID_MATERN12>(p, pl, n, stream);
+    }
+}
+static cudaError_t launch_tc_kv(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
+    switch (pl.kv) {
+        case 1: return launch_tc_kv_k<1>(p, pl, n, stream);
+        case 2: return launch_tc_kv_k<2>(p, pl, n, stream);
+        default: return launch_tc_kv_k<4>(p, pl, n, stream);
+    }
 }
 
 cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packed, int64_t m, int64_t d,
                       const float* V, int64_t k, int64_t ldv, float* Y, int64_t ldy, int kid, float scale,
                       int sm_count, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     TcPlan pl;
-    if (!tc_plan(n, m, d, k, sm_count, &pl, kid)) return cudaErrorInvalidValue;
+    if (!tc_plan(n, m, d, k, sm_count, &pl)) return cudaErrorInvalidValue;
     const size_t v_bytes = (size_t)round_up((int64_t)pl.vimg_bytes, 256);
     if (workspace == nullptr || workspace_bytes < v_bytes + pl.part_bytes) return cudaErrorInvalidValue;
     unsigned char* vimg = static_cast<unsigned char*>(workspace);
@@ -1746,20 +1773,7 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     }
     cudaError_t err;
     if (pl.kv) {
-        const bool m12 = kid == KID_MATERN12;
-        switch (pl.kv) {
-            case 1:
-                err = m12 ? launch_tc_inst<16, 3, true, false, 1>(p, pl, n, stream)
-                          : (pl.nwg == 4 ? launch_tc_inst<16, 4, false, false, 1>(p, pl, n, stream)
-                                         : launch_tc_inst<16, 3, false, false, 1>(p, pl, n, stream));
-                break;
-            case 2:
-                err = m12 ? launch_tc_inst<16, 3, true, false, 2>(p, pl, n, stream) : launch_tc_inst<16, 3, false, false, 2>(p, pl, n, stream);
-                break;
-            default:
-                err = m12 ? launch_tc_inst<16, 3, true, false, 4>(p, pl, n, stream) : launch_tc_inst<16, 3, false, false, 4>(p, pl, n, stream);
-                break;
-        }
+        err = launch_tc_kv(p, pl, n, stream);
     } else
     switch (pl.kp) {
         case 16: err = pl.nwg == 3 ? launch_tc_kp<16, 3>(p, pl, n, stream) : launch_tc_kp<16, 2>(p, pl, n, stream); break;

@@ -280,8 +280,8 @@ def test_register_contraction_against_fp64_oracle(dev, name, n, m, d, k, monkeyp
         assert ko.rel_fro_error(got_t, ref_t) <= (2e-6 if mode == "1" else 1e-5)
 
 
-def test_register_contraction_vector_operand_gather_and_warpgroup_counts(dev, monkeypatch):
-    """1-D operand, row / column index gathers (the SAP / ASkotch oracles), three and four epilogue warpgroups."""
+def test_register_contraction_vector_operand_and_gather(dev, monkeypatch):
+    """1-D operand with row / column index gathers (the SAP / ASkotch oracles), against the oracle and the MMA2 path."""
     from rlaopt_b200._lib import LAYOUT_TC
     from rlaopt_b200.ops import kernel_matmat
 
@@ -290,17 +290,17 @@ def test_register_contraction_vector_operand_gather_and_warpgroup_counts(dev, mo
     v = _rand((n,), 46)
     rows = torch.randperm(n, generator=torch.Generator().manual_seed(47))[:700]
     cols = torch.randperm(n, generator=torch.Generator().manual_seed(48))[:1100]
-    ref = ko.kernel_matmat_gemm_form(X[rows], X[cols], v[cols, None], "rbf", 1.0, dtype=torch.float64)[:, 0]
-    outs = []
-    for nwg in ("4", "3"):
-        monkeypatch.setenv("RLAOPT_B200_TC_NWG", nwg)
-        got = kernel_matmat(X.to(dev), X.to(dev), v[cols].to(dev), "rbf", 1.0, row_idx=rows.to(dev), col_idx=cols.to(dev),
-                            layout=LAYOUT_TC)
-        assert got.shape == (700,)
-        assert ko.rel_fro_error(got, ref) <= 2e-6, nwg
-        outs.append(got)
-    # the warpgroups own different sub-tiles in the two runs: equal up to the order of the partial sums
-    assert ko.rel_fro_error(outs[0], outs[1].double().cpu()) <= 1e-6
+    for name in TC_KERNELS:
+        ref = ko.kernel_matmat_gemm_form(X[rows], X[cols], v[cols, None], name, 1.0, dtype=torch.float64)[:, 0]
+        outs = []
+        for mode in ("1", "0"):
+            monkeypatch.setenv("RLAOPT_B200_TC_KV", mode)
+            got = kernel_matmat(X.to(dev), X.to(dev), v[cols].to(dev), name, 1.0, row_idx=rows.to(dev), col_idx=cols.to(dev),
+                                layout=LAYOUT_TC)
+            assert got.shape == (700,)
+            assert ko.rel_fro_error(got, ref) <= (2e-6 if mode == "1" else 1e-5), (name, mode)
+            outs.append(got)
+        assert ko.rel_fro_error(outs[0], outs[1].double().cpu()) <= 3e-6, name
 
 
 def test_register_contraction_long_positive_sum_and_tiny_values(dev):
