@@ -454,7 +454,6 @@ struct TcParams {
     int nb, la;              // S/P buffers in TMEM; la = extra V-ring depth (V of tile t is consumed la tiles after its A image)
     int wide;                // 1: d > 192, feature-chunked MMA1 with X and Y K-blocks streamed through the A ring
     int pair;                // 1: launched as clusters of two CTAs that share every column-tile load (multicast halves)
-    int prod2;               // 1: the A ring and the V ring are fed by two lanes of the producer warp
     int diag;                // RLAOPT_B200_TC_DIAG knock-outs (-DKMM_TC_PROFILE build only): 1 no MMA, 2 no pointwise, 4 no drain, 8 no loads
     float scale_out;
     int64_t sub_tiles;        // ceil(m / 64)
@@ -608,7 +607,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == TC_EPI_WARPS) {
         // =============================== producer ===============================
-        if (lane == 0 || (lane == 1 && !WIDE && KV == 0 && p.prod2)) {
+        if (lane == 0) {
             const unsigned char* a_src = col_images + (size_t)t_begin * a_img_bytes;
             const unsigned char* v_src = p.vimg + ((size_t)kc * p.sub_tiles + t_begin) * v_img_bytes;
             const float* n_src = col_norms + t_begin * TC_BN;
@@ -673,48 +672,6 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                         }
                     }
                     a_src += (size_t)cnt * a_img_bytes;
-                }
-            } else if (KV == 0 && p.prod2) {
-                // two producer lanes: lane 0 feeds the A ring, lane 1 the V ring -- the barrier polls and copy issues of
-                // the two rings overlap instead of queueing behind each other in one thread
-                if (lane == 0) {
-                    for (int u = 0; u < T; ++u) {
-                        mbar_wait(&a_empty[sa], pha);
-                        mbar_arrive_expect_tx(&a_full[sa], a_img_bytes);
-                        if (!p.pair) {
-                            bulk_copy_g2s(a_ring + (size_t)sa * a_img_bytes, a_src, a_img_bytes, &a_full[sa]);
-                        } else {
-                            const uint32_t a_half = a_img_bytes / 2;
-                            bulk_copy_g2s_mc(a_ring + (size_t)sa * a_img_bytes + crank * a_half, a_src + crank * a_half, a_half,
-                                             &a_full[sa], 3);
-                        }
-                        a_src += a_img_bytes;
-                        if (++sa == SA) {
-                            sa = 0;
-                            pha ^= 1;
-                        }
-                    }
-                } else {
-                    for (int u = 0; u < T; ++u) {
-                        mbar_wait(&v_empty[sv], phv);
-                        unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
-                        mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
-                        if (!p.pair) {
-                            bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
-                            bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
-                        } else if (crank == 0) {
-                            bulk_copy_g2s_mc(vdst, v_src, KP * 128, &v_full[sv], 3);
-                            bulk_copy_g2s_mc(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv], 3);
-                        } else {
-                            bulk_copy_g2s_mc(vdst + KP * 128, v_src + KP * 128, KP * 128 + 16, &v_full[sv], 3);
-                        }
-                        v_src += v_img_bytes;
-                        n_src += TC_BN;
-                        if (++sv == SV) {
-                            sv = 0;
-                            phv ^= 1;
-                        }
-                    }
                 }
             } else
             for (int u = 0; u < T; ++u) {
@@ -1798,7 +1755,6 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     p.nb = pl.nb;
     p.la = pl.la;
     p.diag = tc_env_int("RLAOPT_B200_TC_DIAG", 0);
-    p.prod2 = tc_env_int("RLAOPT_B200_TC_PROD2", 0);
     p.pair = pl.pair;
     p.wide = pl.wide;
     p.kid = kid;
