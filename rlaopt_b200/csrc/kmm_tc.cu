@@ -17,6 +17,11 @@
 //                       buffer: acc += O * 2^-E / s_V with round-to-nearest FFMA2 (the tensor core
 //                       accumulates with truncation, so every sub-tile gets a fresh accumulator)
 //
+// k <= 4 (single right-hand sides) runs in register-contraction mode (template parameter KV): no MMA2 -- the
+// epilogue reads S in the 16x256b fragment pattern (4 rows x 16 columns per thread), evaluates f in fp32 and
+// multiplies with the raw fp32 V tile; warp 10 feeds the V ring instead of issuing MMA2.
+// The X-resident instantiations carry one kernel function each (template parameter KIDT).
+//
 // Split-precision arithmetic (why fp32 parity holds, DESIGN.md "numerics"):
 //   x*s = hi + lo (+2^-22), fp16 pair, s a power of two chosen per operand so |x*s| < 2^13
 //   P*2^E and V*s_V likewise (per row and sub-tile / per 64-row V tile power-of-two scales)
