@@ -94,3 +94,23 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
     assert rc == -1
     with pytest.raises(RuntimeError, match="code -1"):
         _lib.check(rc, "pack_points")
+
+
+def test_register_contraction_workspace_plan(lib, monkeypatch):
+    """k <= 4 on the tensor-core layout: the V workspace is one {V tile, column norms} record of (kv + 1) x 256 B per
+    64-column sub-tile (kv = 1, 2, 4) instead of the fp16 hi/lo image of 16 x 256 + 16 B; RLAOPT_B200_TC_KV=0 switches
+    back.  Host-only: the plan does not touch the GPU."""
+    from rlaopt_b200._lib import LAYOUT_TC
+
+    n, m, d = 1000, 64 * 500 + 1, 16  # one wave: no column splits, no partial buffers
+    sub_tiles = 501
+    monkeypatch.delenv("RLAOPT_B200_TC_KV", raising=False)
+    for k, kv in ((1, 1), (2, 2), (3, 4), (4, 4)):
+        assert lib.rlaopt_b200_matmat_workspace_bytes(n, m, d, k, 4, LAYOUT_TC) == sub_tiles * (kv + 1) * 256
+    image = -(-sub_tiles * (16 * 256 + 16) // 256) * 256
+    assert lib.rlaopt_b200_matmat_workspace_bytes(n, m, d, 5, 4, LAYOUT_TC) == image
+    monkeypatch.setenv("RLAOPT_B200_TC_KV", "0")
+    assert lib.rlaopt_b200_matmat_workspace_bytes(n, m, d, 1, 4, LAYOUT_TC) == image
+    # wide d (X streamed through smem) keeps the MMA2 path
+    monkeypatch.delenv("RLAOPT_B200_TC_KV", raising=False)
+    assert lib.rlaopt_b200_matmat_workspace_bytes(n, m, 500, 1, 4, LAYOUT_TC) >= image  # + split-column partials
