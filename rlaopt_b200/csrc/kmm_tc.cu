@@ -1684,9 +1684,14 @@ static cudaError_t launch_tc_inst(const TcParams& p, const TcPlan& pl, int64_t n
 template <int KP, int NWG>
 static cudaError_t launch_tc_kp(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
     if constexpr (NWG == 2) {
-        if (p.wide)
-            return p.kid == KID_MATERN12 ? launch_tc_inst<KP, NWG, true, true>(p, pl, n, stream)
-                                         : launch_tc_inst<KP, NWG, false, true>(p, pl, n, stream);
+        if (p.wide) {
+            switch (p.kid) {
+                case KID_RBF: return launch_tc_inst<KP, NWG, false, true, 0, KID_RBF>(p, pl, n, stream);
+                case KID_MATERN32: return launch_tc_inst<KP, NWG, false, true, 0, KID_MATERN32>(p, pl, n, stream);
+                case KID_MATERN52: return launch_tc_inst<KP, NWG, false, true, 0, KID_MATERN52>(p, pl, n, stream);
+                default: return launch_tc_inst<KP, NWG, true, true, 0, KID_MATERN12>(p, pl, n, stream);
+            }
+        }
     }
     {
         // X-resident families: one kernel function per instantiation, see KIDT (Matern-1/2, -3/2, -5/2 at d = 32,

@@ -113,6 +113,31 @@ def mid():
         print(f"{name:9s} n={n} m={m} d={d} k={k}: {n * m / sorted(ts)[1] / 1e6:7.1f} Gentries/s", flush=True)
 
 
+def wide():
+    """wide-d instantiations (193 <= d <= 2048): throughput and agreement with the CUDA-core kernel"""
+    from rlaopt_b200._lib import LAYOUT_SIMT
+    for name, n, m, d, k in [("rbf", 32768, 262144, 256, 16), ("matern12", 32768, 262144, 256, 16),
+                             ("matern32", 32768, 262144, 256, 16), ("matern52", 32768, 262144, 256, 16),
+                             ("rbf", 32768, 262144, 784, 1), ("matern52", 16384, 131072, 1024, 64)]:
+        g = torch.Generator().manual_seed(0)
+        A1 = (torch.randn(n, d, generator=g) / d**0.5).to(dev)
+        A2 = (torch.randn(m, d, generator=g) / d**0.5).to(dev)
+        V = torch.randn(m, k, generator=g).to(dev)
+        Y = kernel_matmat(A1, A2, V, name, 1.0, layout=LAYOUT_TC)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            Y = kernel_matmat(A1, A2, V, name, 1.0, layout=LAYOUT_TC)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        R = kernel_matmat(A1[:2048], A2, V, name, 1.0, layout=LAYOUT_SIMT)
+        print(f"{name:9s} n={n} m={m} d={d} k={k}: {n * m / sorted(ts)[1] / 1e6:7.1f} Gentries/s, "
+              f"rel. diff to the CUDA-core kernel on 2048 rows {rel(Y[:2048], R.double()):.2e}", flush=True)
+
+
 def perf():
     for name, n, m, d, k in [("rbf", 131072, 1 << 20, 16, 1), ("rbf", 131072, 1 << 20, 8, 1), ("rbf", 131072, 1 << 20, 32, 2),
                              ("rbf", 131072, 1 << 20, 32, 4), ("matern52", 131072, 1 << 20, 16, 1),
@@ -146,4 +171,4 @@ def perf():
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "acc"
-    {"acc": acc, "perf": perf, "sweep": sweep, "mid": mid}[what]()
+    {"acc": acc, "perf": perf, "sweep": sweep, "mid": mid, "wide": wide}[what]()
