@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RLAOPT_B200_ABI_VERSION 1
+#define RLAOPT_B200_ABI_VERSION 2
 
 /* kernel ids — formulas of rlaopt/kernels/standard.py:46-85 */
 #define RLAOPT_B200_KERNEL_RBF 0      /* exp(-|u|_2^2 / 2)                      standard.py:46-52 */
@@ -76,14 +76,36 @@ int rlaopt_b200_layout_supported(int kernel_id, int elem_bytes, int64_t d, int64
 /* Bytes of the packed form of n points with d features (elem_bytes = 4 or 8). */
 size_t rlaopt_b200_packed_bytes(int64_t n, int64_t d, int elem_bytes, int layout);
 
-/* idx: optional int64 gather list of length n (rows X[idx[i]]), NULL = identity.
- * inv_lengthscale_vec: optional per-feature 1/lengthscale (length d), NULL = use the scalar. */
-int rlaopt_b200_pack_points_f32(const float* X, int64_t n, int64_t d, int64_t ldx, const int64_t* idx,
-                                float inv_lengthscale, const float* inv_lengthscale_vec, int layout,
-                                void* packed, void* stream);
-int rlaopt_b200_pack_points_f64(const double* X, int64_t n, int64_t d, int64_t ldx, const int64_t* idx,
-                                double inv_lengthscale, const double* inv_lengthscale_vec, int layout,
-                                void* packed, void* stream);
+/* X has n_src rows; idx: optional int64 gather list of length n (rows X[idx[i]]; negative entries wrap once
+ * like Python indices; an entry still outside [0, n_src) packs as a zero point and is counted, see
+ * rlaopt_b200_packed_stats_host), NULL = identity (then n <= n_src).
+ * inv_lengthscale_vec: optional per-feature 1/lengthscale (length d), NULL = use the scalar.
+ * center: optional shift (length d, units of X) subtracted from every point before the division by the
+ * lengthscale.  All five kernels are functions of x - y (standard.py:31-43), so the SAME center on both
+ * operands leaves K unchanged; the tensor-core layout needs it for uncentred data, because its GEMM-form
+ * distance |x|^2 + |y|^2 - 2 x.y carries an absolute error ~3e-7 (|x|^2 + |y|^2).  LAYOUT_SIMT forms direct
+ * differences (exact under translation, like the reference's KeOps formula) and ignores it. */
+int rlaopt_b200_pack_points_f32(const float* X, int64_t n, int64_t n_src, int64_t d, int64_t ldx, const int64_t* idx,
+                                float inv_lengthscale, const float* inv_lengthscale_vec, const float* center,
+                                int layout, void* packed, void* stream);
+int rlaopt_b200_pack_points_f64(const double* X, int64_t n, int64_t n_src, int64_t d, int64_t ldx, const int64_t* idx,
+                                double inv_lengthscale, const double* inv_lengthscale_vec, const double* center,
+                                int layout, void* packed, void* stream);
+
+/* Column means of X[idx] (fp64 accumulation, fixed summation order -> bit-reproducible): the center to pass to
+ * both pack calls of one operator (mean of the column operand A2).  workspace: *_workspace_bytes(n, d). */
+size_t rlaopt_b200_column_mean_workspace_bytes(int64_t n, int64_t d);
+int rlaopt_b200_column_mean_f32(const float* X, int64_t n, int64_t n_src, int64_t d, int64_t ldx, const int64_t* idx,
+                                float* center, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Statistics of a LAYOUT_TC pack, copied to HOST memory; synchronises `stream` (the one exception to the
+ * "never synchronises" rule, hence the suffix).  max_sqnorm = max_i |(x_i - center) / lengthscale|^2: the
+ * tensor-core path keeps the 1e-5 parity bar while
+ *     3e-7 * c_kernel * (max_sqnorm(rows) + max_sqnorm(cols)) <= 1e-5,   c = 0.5 RBF, 1.5 Matern-3/2, 5/6 Matern-5/2
+ * beyond that the host falls back to LAYOUT_SIMT (rlaopt_b200.ops.tc_accuracy_ok).  bad_index = number of gather
+ * indices that were out of range.  Either output pointer may be NULL. */
+int rlaopt_b200_packed_stats_host(const void* packed, int layout, float* max_sqnorm_host, int64_t* bad_index_host,
+                                  void* stream);
 
 /* ---------------------------------------------------------------------------
  * Fused matmat on packed operands:  Y[n][k] = const_scaling * K(rows, cols) @ V[m][k].
@@ -111,7 +133,10 @@ int rlaopt_b200_matmat_packed_f64(const void* rows_packed, int64_t n, const void
  *   transpose (transpose = 1): Y[m'][k] = c * K(A1[row_idx], A2[col_idx])^T @ V[n'][k]
  * with n' = n_idx if row_idx else n, m' = m_idx if col_idx else m.
  * This is the whole of _KernelLinOp's matvec / rmatvec / row_oracle / blk_oracle
- * (rlaopt/kernels/base.py:43-47, 104-128) in one call.
+ * (rlaopt/kernels/base.py:43-47, 104-128) in one call.  With LAYOUT_TC the entry centres both operands on
+ * the column means of A2[col_idx] (computed on the device, in the workspace).  It cannot evaluate the accuracy
+ * guard (no synchronisation): callers with unnormalised data (|x / lengthscale|^2 >> 30 after centring) use
+ * LAYOUT_SIMT, or the two-step API with rlaopt_b200_packed_stats_host.
  * ------------------------------------------------------------------------- */
 size_t rlaopt_b200_kernel_matmat_workspace_bytes(int64_t n_rows, int64_t m_cols, int64_t d, int64_t k, int elem_bytes,
                                                  int layout);

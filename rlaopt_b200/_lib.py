@@ -30,12 +30,18 @@ PROTOTYPES = {
     "rlaopt_b200_packed_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
     "rlaopt_b200_pack_points_f32": (
         c_int,
-        [_f32p, c_int64, c_int64, c_int64, _i64p, c_float, _f32p, c_int, c_void_p, c_void_p],
+        [_f32p, c_int64, c_int64, c_int64, c_int64, _i64p, c_float, _f32p, _f32p, c_int, c_void_p, c_void_p],
     ),
     "rlaopt_b200_pack_points_f64": (
         c_int,
-        [_f64p, c_int64, c_int64, c_int64, _i64p, c_double, _f64p, c_int, c_void_p, c_void_p],
+        [_f64p, c_int64, c_int64, c_int64, c_int64, _i64p, c_double, _f64p, _f64p, c_int, c_void_p, c_void_p],
     ),
+    "rlaopt_b200_column_mean_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "rlaopt_b200_column_mean_f32": (
+        c_int,
+        [_f32p, c_int64, c_int64, c_int64, c_int64, _i64p, _f32p, c_void_p, c_size_t, c_void_p],
+    ),
+    "rlaopt_b200_packed_stats_host": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "rlaopt_b200_matmat_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int, c_int]),
     "rlaopt_b200_matmat_packed_f32": (
         c_int,

@@ -1,9 +1,11 @@
 """In-tree build of the C-ABI CUDA library for sm_100a.
 
-    python -m rlaopt_b200.csrc.build [--force]
+    python -m rlaopt_b200.csrc.build [--force] [-v]
 
 nvcc cross-compiles without a GPU; the resulting ``librlaopt_b200.so`` is
-git-ignored but travels to the GPU box with the repo snapshot.
+git-ignored but travels to the GPU box with the repo snapshot.  Every ``.cu`` is
+compiled to its own object (in parallel, re-done only when the file, a header or
+the flags change) and the objects are linked into the shared library.
 """
 from __future__ import annotations
 
@@ -11,31 +13,65 @@ import hashlib
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["kmm_api.cu", "kmm_pack.cu", "kmm_simt.cu", "kmm_tc.cu"]
+SOURCES = ["kmm_api.cu", "kmm_pack.cu", "kmm_simt.cu", "kmm_tc.cu", "kmm_fuse.cu"]
 HEADERS = ["kmm_common.cuh", "kmm_launch.h", "kmm_tmem_ldst.cuh", os.path.join("..", "..", "include", "rlaopt_b200.h")]
 OUT = os.path.join(HERE, "librlaopt_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
+OBJ_DIR = os.path.join(HERE, "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-    "-lcuda",
+    "-Xcompiler", "-fPIC",
 ]
+LINK_FLAGS = ["-shared", "-lcuda"]
 
 
-def _digest() -> str:
+def _nvcc() -> str:
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return nvcc if os.path.exists(nvcc) else "nvcc"
+
+
+def _sources() -> list[str]:
+    return [s for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
+
+
+def _file_digest(names: list[str], extra: str = "") -> str:
     h = hashlib.sha256()
-    for name in SOURCES + HEADERS:
+    for name in names:
         path = os.path.join(HERE, name)
         if os.path.exists(path):
             with open(path, "rb") as f:
                 h.update(name.encode())
                 h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(extra.encode())
     return h.hexdigest()
+
+
+def _digest() -> str:
+    return _file_digest(_sources() + HEADERS, " ".join(NVCC_FLAGS + LINK_FLAGS))
+
+
+def _compile_one(src: str, verbose: bool) -> str:
+    obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+    stamp = obj + ".stamp"
+    digest = _file_digest([src] + HEADERS, " ".join(NVCC_FLAGS))
+    if os.path.exists(obj) and os.path.exists(stamp):
+        with open(stamp) as f:
+            if f.read().strip() == digest:
+                return obj
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    proc = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
+    if verbose or proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed ({proc.returncode}): {' '.join(cmd)}")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return obj
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -44,15 +80,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with open(STAMP) as f:
             if f.read().strip() == digest:
                 return OUT
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    if not os.path.exists(nvcc):
-        nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    if force:
+        for name in os.listdir(OBJ_DIR):
+            if name.endswith(".stamp"):
+                os.remove(os.path.join(OBJ_DIR, name))
+    with ThreadPoolExecutor(max_workers=min(8, len(_sources()))) as pool:
+        objs = list(pool.map(lambda s: _compile_one(s, verbose), _sources()))
+    cmd = [_nvcc()] + ["-gencode", "arch=compute_100a,code=sm_100a"] + LINK_FLAGS + ["-Xcompiler", "-fPIC", "-o", OUT] + objs
     proc = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({proc.returncode}): {' '.join(cmd)}")
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError(f"nvcc link failed ({proc.returncode}): {' '.join(cmd)}")
     with open(STAMP, "w") as f:
         f.write(digest)
     return OUT

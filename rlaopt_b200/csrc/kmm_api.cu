@@ -52,22 +52,27 @@ size_t packed_bytes_t(int64_t n, int64_t d, int layout) {
 }
 
 template <typename T>
-int pack_points_t(const T* X, int64_t n, int64_t d, int64_t ldx, const int64_t* idx, T inv_ls, const T* inv_ls_vec,
-                  int layout, void* packed, void* stream) {
+int pack_points_t(const T* X, int64_t n, int64_t n_src, int64_t d, int64_t ldx, const int64_t* idx, T inv_ls,
+                  const T* inv_ls_vec, const T* center, int layout, void* packed, void* stream) {
     if (n < 0 || d <= 0 || ldx < d) return fail(RLAOPT_B200_EINVAL, "pack_points: bad shape n=%lld d=%lld ldx=%lld",
                                                 (long long)n, (long long)d, (long long)ldx);
+    if (n_src < 0 || (!idx && n > n_src))
+        return fail(RLAOPT_B200_EINVAL, "pack_points: n=%lld points requested from n_src=%lld rows", (long long)n,
+                    (long long)n_src);
     if (n == 0) return 0;
     if (!X || !packed) return fail(RLAOPT_B200_EINVAL, "pack_points: null pointer");
     cudaError_t err;
     if (layout == RLAOPT_B200_LAYOUT_SIMT) {
-        err = kmm::launch_pack<T>(X, n, d, ldx, idx, inv_ls, inv_ls_vec, static_cast<T*>(packed),
+        // direct differences are exact under translation: the shift is not applied on this layout
+        err = kmm::launch_pack<T>(X, n, n_src, d, ldx, idx, inv_ls, inv_ls_vec, static_cast<T*>(packed),
                                   static_cast<cudaStream_t>(stream));
     } else if (layout == RLAOPT_B200_LAYOUT_TC) {
         if constexpr (sizeof(T) == 4) {
             if (!kmm::tc_supported_d(d))
                 return fail(RLAOPT_B200_EUNSUPPORTED, "pack_points: d=%lld not supported by the tensor-core layout",
                             (long long)d);
-            err = kmm::launch_tc_pack(X, n, d, ldx, idx, inv_ls, inv_ls_vec, packed, static_cast<cudaStream_t>(stream));
+            err = kmm::launch_tc_pack(X, n, n_src, d, ldx, idx, inv_ls, inv_ls_vec, center, packed,
+                                      static_cast<cudaStream_t>(stream));
         } else {
             return fail(RLAOPT_B200_EUNSUPPORTED, "pack_points: tensor-core layout is fp32 only");
         }
@@ -144,10 +149,16 @@ int matmat_packed_t(const void* rows, int64_t n, const void* cols, int64_t m, in
     return err == cudaSuccess ? 0 : cuda_fail(err, "matmat");
 }
 
+// one-shot entry, tensor-core layout: d floats for the center + the column-mean partial sums
+size_t center_bytes(int64_t m_cols, int64_t d, int layout) {
+    if (layout != RLAOPT_B200_LAYOUT_TC) return 0;
+    return align256((size_t)d * sizeof(float)) + align256(kmm::column_mean_workspace_bytes(m_cols, d));
+}
+
 template <typename T>
 size_t oneshot_workspace_t(int64_t n_rows, int64_t m_cols, int64_t d, int64_t k, int layout) {
     return align256(packed_bytes_t<T>(n_rows, d, layout)) + align256(packed_bytes_t<T>(m_cols, d, layout)) +
-           align256(matmat_workspace_t<T>(n_rows, m_cols, d, k, layout));
+           align256(matmat_workspace_t<T>(n_rows, m_cols, d, k, layout)) + center_bytes(m_cols, d, layout);
 }
 
 template <typename T>
@@ -162,16 +173,32 @@ int oneshot_t(const T* A1, int64_t n, int64_t lda1, const T* A2, int64_t m, int6
     const int64_t red_cols = transpose ? n_eff : m_eff;
     const size_t pb1 = align256(packed_bytes_t<T>(n_eff, d, layout));
     const size_t pb2 = align256(packed_bytes_t<T>(m_eff, d, layout));
-    const size_t mm = matmat_workspace_t<T>(out_rows, red_cols, d, k, layout);
-    if (pb1 + pb2 + mm > ws_bytes || (pb1 + pb2 + mm > 0 && !ws))
-        return fail(RLAOPT_B200_EWORKSPACE, "kernel_matmat: workspace %zu < required %zu bytes", ws_bytes, pb1 + pb2 + mm);
+    const size_t mm = align256(matmat_workspace_t<T>(out_rows, red_cols, d, k, layout));
+    const size_t cb = center_bytes(m_eff, d, layout);
+    if (pb1 + pb2 + mm + cb > ws_bytes || (pb1 + pb2 + mm + cb > 0 && !ws))
+        return fail(RLAOPT_B200_EWORKSPACE, "kernel_matmat: workspace %zu < required %zu bytes", ws_bytes,
+                    pb1 + pb2 + mm + cb);
+    if (n_eff == 0 || m_eff == 0)  // empty operand: nothing to pack; the product is an empty sum
+        return matmat_packed_t<T>(nullptr, out_rows, nullptr, red_cols, d, V, k, ldv, Y, ldy, kid, scale, layout,
+                                  nullptr, 0, stream);
     unsigned char* base = static_cast<unsigned char*>(ws);
     void* p1 = base;
     void* p2 = base + pb1;
     void* pw = base + pb1 + pb2;
-    int rc = pack_points_t<T>(A1, n_eff, d, lda1, row_idx, inv_ls, inv_ls_vec, layout, p1, stream);
+    const T* center = nullptr;
+    if constexpr (sizeof(T) == 4) {
+        if (cb > 0) {  // tensor-core layout: both operands are shifted by the column means of A2[col_idx]
+            float* c = reinterpret_cast<float*>(base + pb1 + pb2 + mm);
+            cudaError_t err = kmm::launch_column_mean(A2, m_eff, m, d, lda2, col_idx, c,
+                                                      base + pb1 + pb2 + mm + align256((size_t)d * sizeof(float)),
+                                                      static_cast<cudaStream_t>(stream));
+            if (err != cudaSuccess) return cuda_fail(err, "kernel_matmat(column_mean)");
+            center = c;
+        }
+    }
+    int rc = pack_points_t<T>(A1, n_eff, n, d, lda1, row_idx, inv_ls, inv_ls_vec, center, layout, p1, stream);
     if (rc) return rc;
-    rc = pack_points_t<T>(A2, m_eff, d, lda2, col_idx, inv_ls, inv_ls_vec, layout, p2, stream);
+    rc = pack_points_t<T>(A2, m_eff, m, d, lda2, col_idx, inv_ls, inv_ls_vec, center, layout, p2, stream);
     if (rc) return rc;
     if (transpose)
         return matmat_packed_t<T>(p2, m_eff, p1, n_eff, d, V, k, ldv, Y, ldy, kid, scale, layout, pw, mm, stream);
@@ -198,15 +225,48 @@ size_t rlaopt_b200_packed_bytes(int64_t n, int64_t d, int elem_bytes, int layout
     return elem_bytes == 8 ? packed_bytes_t<double>(n, d, layout) : packed_bytes_t<float>(n, d, layout);
 }
 
-int rlaopt_b200_pack_points_f32(const float* X, int64_t n, int64_t d, int64_t ldx, const int64_t* idx,
-                                float inv_lengthscale, const float* inv_lengthscale_vec, int layout, void* packed,
-                                void* stream) {
-    return pack_points_t<float>(X, n, d, ldx, idx, inv_lengthscale, inv_lengthscale_vec, layout, packed, stream);
+int rlaopt_b200_pack_points_f32(const float* X, int64_t n, int64_t n_src, int64_t d, int64_t ldx, const int64_t* idx,
+                                float inv_lengthscale, const float* inv_lengthscale_vec, const float* center,
+                                int layout, void* packed, void* stream) {
+    return pack_points_t<float>(X, n, n_src, d, ldx, idx, inv_lengthscale, inv_lengthscale_vec, center, layout, packed,
+                                stream);
 }
-int rlaopt_b200_pack_points_f64(const double* X, int64_t n, int64_t d, int64_t ldx, const int64_t* idx,
-                                double inv_lengthscale, const double* inv_lengthscale_vec, int layout, void* packed,
-                                void* stream) {
-    return pack_points_t<double>(X, n, d, ldx, idx, inv_lengthscale, inv_lengthscale_vec, layout, packed, stream);
+int rlaopt_b200_pack_points_f64(const double* X, int64_t n, int64_t n_src, int64_t d, int64_t ldx, const int64_t* idx,
+                                double inv_lengthscale, const double* inv_lengthscale_vec, const double* center,
+                                int layout, void* packed, void* stream) {
+    return pack_points_t<double>(X, n, n_src, d, ldx, idx, inv_lengthscale, inv_lengthscale_vec, center, layout,
+                                 packed, stream);
+}
+
+size_t rlaopt_b200_column_mean_workspace_bytes(int64_t n, int64_t d) { return kmm::column_mean_workspace_bytes(n, d); }
+
+int rlaopt_b200_column_mean_f32(const float* X, int64_t n, int64_t n_src, int64_t d, int64_t ldx, const int64_t* idx,
+                                float* center, void* workspace, size_t workspace_bytes, void* stream) {
+    if (n <= 0 || d <= 0 || ldx < d || n_src < 0 || (!idx && n > n_src))
+        return fail(RLAOPT_B200_EINVAL, "column_mean: bad shape n=%lld n_src=%lld d=%lld ldx=%lld", (long long)n,
+                    (long long)n_src, (long long)d, (long long)ldx);
+    if (!X || !center) return fail(RLAOPT_B200_EINVAL, "column_mean: null pointer");
+    const size_t need = kmm::column_mean_workspace_bytes(n, d);
+    if (!workspace || workspace_bytes < need)
+        return fail(RLAOPT_B200_EWORKSPACE, "column_mean: workspace %zu < required %zu bytes", workspace_bytes, need);
+    cudaError_t err = kmm::launch_column_mean(X, n, n_src, d, ldx, idx, center, workspace, static_cast<cudaStream_t>(stream));
+    return err == cudaSuccess ? 0 : cuda_fail(err, "column_mean");
+}
+
+int rlaopt_b200_packed_stats_host(const void* packed, int layout, float* max_sqnorm_host, int64_t* bad_index_host,
+                                  void* stream) {
+    if (layout != RLAOPT_B200_LAYOUT_TC)
+        return fail(RLAOPT_B200_EUNSUPPORTED, "packed_stats: only the tensor-core layout carries statistics");
+    if (!packed) return fail(RLAOPT_B200_EINVAL, "packed_stats: null pointer");
+    unsigned int words[2] = {0u, 0u};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t err = cudaMemcpyAsync(words, static_cast<const unsigned char*>(packed) + kmm::tc_stats_offset(),
+                                      sizeof(words), cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) return cuda_fail(err, "packed_stats");
+    if (max_sqnorm_host) memcpy(max_sqnorm_host, &words[0], sizeof(float));
+    if (bad_index_host) *bad_index_host = (int64_t)words[1];
+    return 0;
 }
 
 size_t rlaopt_b200_matmat_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int elem_bytes, int layout) {

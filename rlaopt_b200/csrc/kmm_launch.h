@@ -8,9 +8,15 @@
 namespace kmm {
 
 // ---- packing (kmm_pack.cu): row-major points -> feature-major, 1/lengthscale applied ----
+// idx: optional gather list (negative entries wrap once, out-of-range entries pack as zero points)
 template <typename T>
-cudaError_t launch_pack(const T* X, int64_t n, int64_t d, int64_t ldx, const int64_t* idx, T inv_ls,
+cudaError_t launch_pack(const T* X, int64_t n, int64_t n_src, int64_t d, int64_t ldx, const int64_t* idx, T inv_ls,
                         const T* inv_ls_vec, T* packed, cudaStream_t stream);
+
+// column means of X[idx] (fp64 accumulation, fixed summation order): the common shift of the tensor-core packs
+size_t column_mean_workspace_bytes(int64_t n, int64_t d);
+cudaError_t launch_column_mean(const float* X, int64_t n, int64_t n_src, int64_t d, int64_t ldx, const int64_t* idx,
+                               float* center, void* workspace, cudaStream_t stream);
 
 // ---- CUDA-core fused matmat (kmm_simt.cu) ----
 template <typename T>
@@ -44,8 +50,10 @@ cudaError_t launch_split_reduce(const T* part, int splits, int64_t n, int64_t k,
 bool tc_supported_d(int64_t d);
 bool tc_supported_k(int64_t k);
 size_t tc_packed_bytes(int64_t n, int64_t d);
-cudaError_t launch_tc_pack(const float* X, int64_t n, int64_t d, int64_t ldx, const int64_t* idx, float inv_ls,
-                           const float* inv_ls_vec, void* packed, cudaStream_t stream);
+cudaError_t launch_tc_pack(const float* X, int64_t n, int64_t n_src, int64_t d, int64_t ldx, const int64_t* idx,
+                           float inv_ls, const float* inv_ls_vec, const float* center, void* packed,
+                           cudaStream_t stream);
+size_t tc_stats_offset();  // byte offset of {max squared norm (float bits), bad-index count} in a packed operand
 size_t tc_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count);
 cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packed, int64_t m, int64_t d,
                       const float* V, int64_t k, int64_t ldv, float* Y, int64_t ldy, int kid, float scale,

@@ -331,13 +331,9 @@ cudaError_t launch_one(const SimtArgs<T>& a, int splits, int tiles_per_split, T*
                        int64_t split_stride, T scale) {
     using Smem = SimtSmem<T, KC>;
     auto kern = kmm_simt_kernel<T, L1, KC>;
-    static bool configured = false;  // per instantiation; attribute is per-device-context but cheap to reset
-    cudaError_t err;
-    if (!configured || true) {
-        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        if (err != cudaSuccess) return err;
-        configured = true;
-    }
+    // the attribute lives in the device context (one per GPU of a multi-device process): set it on every launch
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (err != cudaSuccess) return err;
     const int64_t row_tiles = (a.n + BM - 1) / BM;
     const int k_chunks = (int)((a.k + KC - 1) / KC);
     dim3 grid((unsigned)row_tiles, (unsigned)k_chunks, (unsigned)splits);

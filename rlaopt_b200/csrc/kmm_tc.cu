@@ -27,6 +27,7 @@
 //   P*2^E and V*s_V likewise (per row and sub-tile / per 64-row V tile power-of-two scales)
 // K is never written to HBM; S and P never leave TMEM / registers.
 #include <cuda_fp16.h>
+#include <stddef.h>
 #include <stdlib.h>
 
 #include "kmm_common.cuh"
@@ -50,9 +51,11 @@ constexpr uint32_t TC_WIDE_STAGE_BYTES = 8 * TC_KBLOCK_BYTES;  // {X hi, X lo, Y
 constexpr int TC_SMEM_LIMIT = 220 * 1024;
 
 struct TcHeader {
-    unsigned int absmax_bits;  // max |x / lengthscale| as float bits (filled by the absmax kernel)
+    unsigned int absmax_bits;  // max |(x - center) / lengthscale| as float bits (filled by the absmax kernel)
     float scale;               // power of two s with |x * s| in [2^12, 2^13)
     float inv_scale;
+    unsigned int max_sqnorm_bits;  // max_i |(x_i - center) / lengthscale|^2 as float bits: the accuracy guard of the host
+    unsigned int bad_index;        // number of gather indices outside [-n_src, n_src) (packed as zero points)
 };
 
 __host__ __device__ inline int tc_kblocks(int64_t d) { return (int)((d + 63) / 64); }
@@ -298,26 +301,40 @@ __device__ __noinline__ float tc_exact_dist2(const unsigned char* xi, int swx, c
 // ------------------------------------------------------------------------------------------
 // packing kernels
 // ------------------------------------------------------------------------------------------
-__global__ void tc_absmax_kernel(const float* __restrict__ X, int64_t n, int64_t d, int64_t ldx,
+// gather index with Python semantics: negative indices wrap once; anything still outside [0, n_src) is invalid (-1)
+__device__ __forceinline__ int64_t tc_src_row(const int64_t* __restrict__ idx, int64_t i, int64_t n_src) {
+    if (!idx) return i;
+    int64_t s = idx[i];
+    if (s < 0) s += n_src;
+    return (s >= 0 && s < n_src) ? s : -1;
+}
+
+__global__ void tc_absmax_kernel(const float* __restrict__ X, int64_t n, int64_t n_src, int64_t d, int64_t ldx,
                                  const int64_t* __restrict__ idx, float inv_ls, const float* __restrict__ inv_ls_vec,
-                                 TcHeader* hdr) {
+                                 const float* __restrict__ center, TcHeader* hdr) {
     float mx = 0.0f;
     const int64_t total = n * d;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = e / d, f = e % d;
-        const int64_t src = idx ? idx[i] : i;
+        const int64_t src = tc_src_row(idx, i, n_src);
+        if (src < 0) continue;
         const float s = inv_ls_vec ? inv_ls_vec[f] : inv_ls;
-        const float v = fabsf(X[src * ldx + f] * s);
+        const float c = center ? center[f] : 0.0f;
+        const float v = fabsf((X[src * ldx + f] - c) * s);
         if (v < 3.0e38f) mx = fmaxf(mx, v);  // ignore inf / nan here; they propagate through the values
     }
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0 && mx > 0.0f) atomicMax(&hdr->absmax_bits, __float_as_uint(mx));
 }
 
-// one thread per (padded) point: fp16 hi/lo split into the swizzled tile image + squared norm
-__global__ void tc_pack_points_kernel(const float* __restrict__ X, int64_t n, int64_t d, int64_t ldx,
+// one thread per (padded) point: fp16 hi/lo split into the swizzled tile image + squared norm.
+// `center` (optional, one value per feature, in the units of X): every kernel here is a function of x - y, so the
+// same vector subtracted from both operands leaves K unchanged while it shrinks |x|^2 + |y|^2 -- and with it the
+// absolute error eps (|x|^2 + |y|^2) of the GEMM-form distance.
+__global__ void tc_pack_points_kernel(const float* __restrict__ X, int64_t n, int64_t n_src, int64_t d, int64_t ldx,
                                       const int64_t* __restrict__ idx, float inv_ls,
-                                      const float* __restrict__ inv_ls_vec, unsigned char* __restrict__ packed, int kb_count) {
+                                      const float* __restrict__ inv_ls_vec, const float* __restrict__ center,
+                                      unsigned char* __restrict__ packed, int kb_count) {
     TcHeader* hdr = reinterpret_cast<TcHeader*>(packed);
     const float absmax = __uint_as_float(hdr->absmax_bits);
     float s = 1.0f;
@@ -332,7 +349,8 @@ __global__ void tc_pack_points_kernel(const float* __restrict__ X, int64_t n, in
     float* norms = reinterpret_cast<float*>(packed + tc_norm_offset());
     unsigned char* img = packed + tc_image_offset(n) + (size_t)(i >> 6) * tc_image_bytes(kb_count);
     const int r = (int)(i & 63);
-    const int64_t src = (i < n) ? (idx ? idx[i] : i) : 0;
+    const int64_t src = (i < n) ? tc_src_row(idx, i, n_src) : -1;
+    if (i < n && src < 0) atomicAdd(&hdr->bad_index, 1u);
     double nrm = 0.0;
     for (int kb = 0; kb < kb_count; ++kb) {
         for (int c = 0; c < 8; ++c) {
@@ -342,7 +360,8 @@ __global__ void tc_pack_points_kernel(const float* __restrict__ X, int64_t n, in
             for (int e = 0; e < 8; ++e) {
                 const int64_t f = (int64_t)kb * 64 + c * 8 + e;
                 float v = 0.0f;
-                if (i < n && f < d) v = X[src * ldx + f] * (inv_ls_vec ? inv_ls_vec[f] : inv_ls) * s;
+                if (src >= 0 && f < d)
+                    v = (X[src * ldx + f] - (center ? center[f] : 0.0f)) * (inv_ls_vec ? inv_ls_vec[f] : inv_ls) * s;
                 const __half h = __float2half_rn(v);
                 const __half l = __float2half_rn(v - __half2float(h));
                 hi[e] = h;
@@ -355,7 +374,12 @@ __global__ void tc_pack_points_kernel(const float* __restrict__ X, int64_t n, in
             *reinterpret_cast<uint4*>(img + (size_t)kb_count * TC_KBLOCK_BYTES + off) = *reinterpret_cast<const uint4*>(lo);
         }
     }
-    norms[i] = (float)(nrm / ((double)s * (double)s));
+    const float nrm_f = (float)(nrm / ((double)s * (double)s));
+    norms[i] = nrm_f;
+    // accuracy guard input: the largest squared norm of the set (non-negative floats order like their bit patterns)
+    float wmax = (nrm_f < 3.0e38f) ? nrm_f : 0.0f;
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if ((threadIdx.x & 31) == 0 && wmax > 0.0f) atomicMax(&hdr->max_sqnorm_bits, __float_as_uint(wmax));
 }
 
 // V[m][k] -> per (k-chunk, 64-row sub-tile) image of the MMA2 B operand, one block per image:
@@ -1639,19 +1663,24 @@ size_t tc_packed_bytes(int64_t n, int64_t d) {
     return tc_image_offset(n) + (size_t)(tc_npad(n) / 64) * tc_image_bytes(tc_kblocks(d));
 }
 
-cudaError_t launch_tc_pack(const float* X, int64_t n, int64_t d, int64_t ldx, const int64_t* idx, float inv_ls,
-                           const float* inv_ls_vec, void* packed, cudaStream_t stream) {
+cudaError_t launch_tc_pack(const float* X, int64_t n, int64_t n_src, int64_t d, int64_t ldx, const int64_t* idx,
+                           float inv_ls, const float* inv_ls_vec, const float* center, void* packed,
+                           cudaStream_t stream) {
     cudaError_t err = cudaMemsetAsync(packed, 0, TC_HEADER_BYTES, stream);
     if (err != cudaSuccess) return err;
     const int64_t total = n * d;
     int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
     if (blocks < 1) blocks = 1;
-    tc_absmax_kernel<<<blocks, 256, 0, stream>>>(X, n, d, ldx, idx, inv_ls, inv_ls_vec, reinterpret_cast<TcHeader*>(packed));
+    tc_absmax_kernel<<<blocks, 256, 0, stream>>>(X, n, n_src, d, ldx, idx, inv_ls, inv_ls_vec, center,
+                                                 reinterpret_cast<TcHeader*>(packed));
     const int64_t n_pad = tc_npad(n);
     tc_pack_points_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, stream>>>(
-        X, n, d, ldx, idx, inv_ls, inv_ls_vec, static_cast<unsigned char*>(packed), tc_kblocks(d));
+        X, n, n_src, d, ldx, idx, inv_ls, inv_ls_vec, center, static_cast<unsigned char*>(packed), tc_kblocks(d));
     return cudaGetLastError();
 }
+
+// header fields the host reads back for its accuracy guard / index check (the copy is the caller's)
+size_t tc_stats_offset() { return offsetof(TcHeader, max_sqnorm_bits); }
 
 size_t tc_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count) {
     TcPlan pl;

@@ -45,39 +45,103 @@ def _n_cols(x: torch.Tensor) -> int:
     return 1 if x.ndim == 1 else x.shape[1]
 
 
-class _PackCache:
-    """Packed forms of (A1, A2) per kernel layout; A1 is A2 shares one pack."""
+def _ls_state(lengthscale):
+    """Identity + in-place version of a lengthscale (tensor) or its value (float)."""
+    if isinstance(lengthscale, torch.Tensor):
+        return (id(lengthscale), lengthscale._version)
+    return float(lengthscale)
 
-    def __init__(self, A1: torch.Tensor, A2: torch.Tensor, lengthscale):
-        self.A1, self.A2, self.lengthscale = A1, A2, lengthscale
+
+class _PackCache:
+    """Packed forms of (A1, A2) per kernel layout; ``A1 is A2`` shares one pack.
+
+    Tensor-core packs are shifted by one common center, the column means of ``A2`` (all kernels are functions of
+    ``x - y``, ``rlaopt/kernels/standard.py:31-43``, so K is unchanged).  The reference's LazyTensor reads the live
+    tensors on every product; the packs are snapshots, so they are keyed on the in-place versions of ``A1``, ``A2``
+    and the lengthscale and rebuilt when any of them was modified.
+    """
+
+    def __init__(self, A1: torch.Tensor, A2: torch.Tensor, kernel_config):
+        self.A1, self.A2, self.cfg = A1, A2, kernel_config
         self.shared = _same_storage(A1, A2)
         self._rows: dict[int, object] = {}
         self._cols: dict[int, object] = {}
+        self._center: Optional[torch.Tensor] = None
+        self._tc_ok: dict[int, bool] = {}
+        self._state = self._live_state()
+
+    @property
+    def lengthscale(self):
+        return self.cfg.lengthscale
+
+    def _live_state(self):
+        return (self.A1._version, self.A2._version, _ls_state(self.cfg.lengthscale))
+
+    def validate(self) -> None:
+        """Drop every pack if A1, A2 or the lengthscale changed since they were built."""
+        state = self._live_state()
+        if state != self._state:
+            self.clear()
+            self._state = state
+
+    def center(self) -> Optional[torch.Tensor]:
+        """Common shift of the tensor-core packs (fp32 only; ``None`` for fp64 operators)."""
+        self.validate()
+        if self._center is None and self.A2.dtype == torch.float32 and self.A2.is_cuda:
+            self._center = ops.column_mean(self.A2)
+        return self._center
+
+    def _pack(self, A: torch.Tensor, layout: int):
+        return ops.pack_points(A, self.lengthscale, None, layout, self.center() if layout == ops.LAYOUT_TC else None)
 
     def rows(self, layout: int):
         """Pack of A1 (built on first use; shared with the column pack when A1 is A2)."""
+        self.validate()
         if layout not in self._rows:
             if self.shared and layout in self._cols:
                 self._rows[layout] = self._cols[layout]
             else:
-                self._rows[layout] = ops.pack_points(self.A1, self.lengthscale, None, layout)
+                self._rows[layout] = self._pack(self.A1, layout)
         return self._rows[layout]
 
     def cols(self, layout: int):
         """Pack of A2 alone -- all a row oracle needs (its rows are gathered per block)."""
+        self.validate()
         if layout not in self._cols:
             if self.shared and layout in self._rows:
                 self._cols[layout] = self._rows[layout]
             else:
-                self._cols[layout] = ops.pack_points(self.A2, self.lengthscale, None, layout)
+                self._cols[layout] = self._pack(self.A2, layout)
         return self._cols[layout]
 
     def get(self, layout: int):
         return self.rows(layout), self.cols(layout)
 
+    def known_sqnorm(self, which: str) -> Optional[float]:
+        """Largest centred squared norm of A1 / A2 if its tensor-core pack exists (an upper bound for any row
+        subset packed with the same center), else ``None``."""
+        packs = self._rows if which == "rows" else self._cols
+        other = self._cols if which == "rows" else self._rows
+        P = packs.get(ops.LAYOUT_TC) or (other.get(ops.LAYOUT_TC) if self.shared else None)
+        return None if P is None else P.max_sqnorm
+
+    def tc_ok(self, kid: int) -> bool:
+        """Data-dependent half of the layout choice for the full operator (one 8-byte read-back per operator)."""
+        self.validate()
+        if kid not in self._tc_ok:
+            P1, P2 = self.get(ops.LAYOUT_TC)
+            ok = ops.tc_accuracy_ok(kid, P1.max_sqnorm, P2.max_sqnorm)
+            self._tc_ok[kid] = ok
+            if not ok:  # the tensor-core packs will not be used: release them
+                self._rows.pop(ops.LAYOUT_TC, None)
+                self._cols.pop(ops.LAYOUT_TC, None)
+        return self._tc_ok[kid]
+
     def clear(self) -> None:
         self._rows.clear()
         self._cols.clear()
+        self._center = None
+        self._tc_ok.clear()
 
 
 class _KernelLinOp(TwoSidedLinOp, ScaleMixin):
@@ -90,7 +154,7 @@ class _KernelLinOp(TwoSidedLinOp, ScaleMixin):
         self._kernel_key = _kernel_key
         self._kernel_id = ops.kernel_id(_kernel_key)
         self._initialize_scaling(getattr(kernel_config, "const_scaling", 1.0))
-        self._cache = _PackCache(A1, A2, kernel_config.lengthscale)
+        self._cache = _PackCache(A1, A2, kernel_config)
         self._oracle_memo: dict[str, tuple] = {}
         super().__init__(
             device=A1.device,
@@ -134,7 +198,12 @@ class _KernelLinOp(TwoSidedLinOp, ScaleMixin):
 
     # -- products -----------------------------------------------------------
     def _layout_for(self, x: torch.Tensor) -> int:
-        return ops.choose_layout(self._kernel_id, self._A1.dtype, self._A1.shape[1], _n_cols(x))
+        """Shape rule (``ops.choose_layout``) plus the accuracy guard of the tensor-core path: data whose centred,
+        lengthscale-scaled norms exceed the budget of ``ops.tc_accuracy_ok`` runs on the direct-difference kernel."""
+        layout = ops.choose_layout(self._kernel_id, self._A1.dtype, self._A1.shape[1], _n_cols(x))
+        if layout == ops.LAYOUT_TC and not self._cache.tc_ok(self._kernel_id):
+            return ops.LAYOUT_SIMT
+        return layout
 
     def _forward(self, x: torch.Tensor) -> torch.Tensor:
         P1, P2 = self._cache.get(self._layout_for(x))
@@ -146,24 +215,45 @@ class _KernelLinOp(TwoSidedLinOp, ScaleMixin):
         return ops.matmat_packed(P2, P1, x, self._kernel_id, self._scaling)
 
     # -- oracles --------------------------------------------------------------
-    def _oracle_packs(self, kind: str, blk: torch.Tensor, layout: int):
+    def _oracle_packs(self, kind: str, blk: torch.Tensor, x: torch.Tensor):
         """Packs of ``A1[blk]`` (and ``A2[blk]``), memoised on the identity of ``blk``.
 
         SAP asks for ``A_blk_oracle(blk)`` once per power-iteration matvec with the
         same ``blk`` object (``rlaopt/solvers/sap.py:96-97``); the memo turns those
-        repeats into cache hits.
+        repeats into cache hits.  The blocks are packed with the operator's center, so the
+        operator's norm bound covers them (no read-back per block when ``A1 is A2``).
         """
+        cache = self._cache
+        cache.validate()
+        layout = ops.choose_layout(self._kernel_id, self._A1.dtype, self._A1.shape[1], _n_cols(x))
         key = f"{kind}:{layout}"
         memo = self._oracle_memo.get(key)
-        if memo is not None and memo[0] is blk and memo[1] == blk._version:
+        if memo is not None and memo[0] is blk and memo[1] == (blk._version, cache._state):
             return memo[2]
-        Pr = ops.pack_points(self._A1, self._kernel_config.lengthscale, blk, layout)
-        if kind == "row":
-            packs = (Pr, self._cache.cols(layout))
-        else:
-            Pc = Pr if self._cache.shared else ops.pack_points(self._A2, self._kernel_config.lengthscale, blk, layout)
-            packs = (Pr, Pc)
-        self._oracle_memo[key] = (blk, blk._version, packs)
+        ls = self._kernel_config.lengthscale
+        packs = None
+        if layout == ops.LAYOUT_TC:
+            c = cache.center()
+            Pr = ops.pack_points(self._A1, ls, blk, layout, c)
+            if kind == "row":
+                Pc = cache.cols(layout)
+            else:
+                Pc = Pr if cache.shared else ops.pack_points(self._A2, ls, blk, layout, c)
+            rmax, cmax = cache.known_sqnorm("rows"), cache.known_sqnorm("cols")
+            if rmax is None or cmax is None or not ops.tc_accuracy_ok(self._kernel_id, rmax, cmax):
+                # no operator-wide bound (or it fails): this block's own norms decide
+                rmax, cmax = Pr.max_sqnorm, Pc.max_sqnorm
+            if ops.tc_accuracy_ok(self._kernel_id, rmax, cmax):
+                packs = (Pr, Pc)
+            else:
+                layout = ops.LAYOUT_SIMT
+        if packs is None:
+            Pr = ops.pack_points(self._A1, ls, blk, layout)
+            if kind == "row":
+                packs = (Pr, cache.cols(layout))
+            else:
+                packs = (Pr, Pr if cache.shared else ops.pack_points(self._A2, ls, blk, layout))
+        self._oracle_memo[key] = (blk, (blk._version, cache._state), packs)
         return packs
 
     def _get_kernel_linop(self, kind: str, blk: torch.Tensor) -> LinOp:
@@ -172,7 +262,7 @@ class _KernelLinOp(TwoSidedLinOp, ScaleMixin):
         n_cols = blk.shape[0] if kind == "blk" else self._A2.shape[0]
 
         def matvec(x: torch.Tensor) -> torch.Tensor:
-            Pr, Pc = self._oracle_packs(kind, blk, self._layout_for(x))
+            Pr, Pc = self._oracle_packs(kind, blk, x)
             return ops.matmat_packed(Pr, Pc, x, self._kernel_id, self._scaling)
 
         return LinOp(
@@ -306,13 +396,22 @@ class _DistributedKernelLinOp(DistributedTwoSidedLinOp, ScaleMixin):
             raise ValueError("All elements in devices must be torch.device instances.")
 
     # -- oracles ------------------------------------------------------------
+    def _chunk_center(self, i: int) -> torch.Tensor:
+        """Shift of the tensor-core packs on device ``i``: the column means of its resident A2 chunk.  Any vector
+        works as long as the row and column operand of one product share it; partial products are summed after."""
+        cache = self._A2_chunk_packs[i]
+        if "center" not in cache:
+            cache["center"] = ops.column_mean(self.A2_chunks[i])
+        return cache["center"]
+
     def _chunk_pack(self, i: int, layout: int):
         """Pack of the i-th A2 column block on its device (cached across oracle calls)."""
         cache = self._A2_chunk_packs[i]
         if layout not in cache:
             dev = self.A2_chunks[i].device
             cache[layout] = ops.pack_points(
-                self.A2_chunks[i], self._kernel_config_devices[dev].lengthscale, None, layout
+                self.A2_chunks[i], self._kernel_config_devices[dev].lengthscale, None, layout,
+                self._chunk_center(i) if layout == ops.LAYOUT_TC else None,
             )
         return cache[layout]
 
@@ -392,18 +491,29 @@ class _ShardProduct:
         self.kid, self.scale, self.d, self.dtype = kid, scale, d, dtype
         self._packs: dict[int, tuple] = {}
 
-    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+    def _build(self, layout: int):
         owner, i, dev = self.owner, self.i, self.dev
+        ls = owner._kernel_config_devices[dev].lengthscale
+        rows = self.rows.to(dev)
+        tc = layout == ops.LAYOUT_TC
+        if self.cols is None:
+            Pc = owner._chunk_pack(i, layout)
+            Pr = ops.pack_points(rows, ls, None, layout, Pc.center)
+        elif self.cols is self.rows:
+            Pr = Pc = ops.pack_points(rows, ls, None, layout, ops.column_mean(rows) if tc else None)
+        else:
+            cols = self.cols.to(dev)
+            c = ops.column_mean(cols) if tc else None
+            Pr = ops.pack_points(rows, ls, None, layout, c)
+            Pc = ops.pack_points(cols, ls, None, layout, c)
+        return Pr, Pc
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
         layout = ops.choose_layout(self.kid, self.dtype, self.d, _n_cols(x))
         if layout not in self._packs:
-            ls = owner._kernel_config_devices[dev].lengthscale
-            Pr = ops.pack_points(self.rows.to(dev), ls, None, layout)
-            if self.cols is None:
-                Pc = owner._chunk_pack(i, layout)
-            elif self.cols is self.rows:
-                Pc = Pr
-            else:
-                Pc = ops.pack_points(self.cols.to(dev), ls, None, layout)
+            Pr, Pc = self._build(layout)
+            if layout == ops.LAYOUT_TC and not ops.tc_accuracy_ok(self.kid, Pr.max_sqnorm, Pc.max_sqnorm):
+                Pr, Pc = self._build(ops.LAYOUT_SIMT)  # norms beyond the tensor-core accuracy budget
             self._packs[layout] = (Pr, Pc)
         Pr, Pc = self._packs[layout]
         return ops.matmat_packed(Pr, Pc, x, self.kid, self.scale)

@@ -77,15 +77,31 @@ class ShardedKernelLinOp(RowShardedLinOp):
         lo, hi = shard_rows(b, self.world)[self.rank]
         mine = blk_dev[lo:hi]
         block = -(-b // self.world)
-        cfg, kernel, A1, A2, group, world = self._cfg, self._kernel, self._A1, self._A2, self.group, self.world
+        cfg, A1, A2, group, world = self._cfg, self._A1, self._A2, self.group, self.world
+        kid = ops.kernel_id(self._kernel)
+        packs: dict[int, tuple] = {}  # per layout: this rank's rows of the block and the whole block, packed once
+
+        def block_packs(k: int):
+            layout = ops.choose_layout(kid, A1.dtype, A1.shape[1], k)
+            if layout not in packs:
+                def build(lay):
+                    c = ops.column_mean(A2, blk_dev) if lay == ops.LAYOUT_TC else None
+                    return (ops.pack_points(A1, cfg.lengthscale, mine, lay, c),
+                            ops.pack_points(A2, cfg.lengthscale, blk_dev, lay, c))
+                Pr, Pc = build(layout)
+                if layout == ops.LAYOUT_TC and not ops.tc_accuracy_ok(kid, Pr.max_sqnorm, Pc.max_sqnorm):
+                    Pr, Pc = build(ops.LAYOUT_SIMT)
+                packs[layout] = (Pr, Pc)
+            return packs[layout]
 
         def matmat(x: torch.Tensor) -> torch.Tensor:
             vec = x.ndim == 1
             xm = x.unsqueeze(1) if vec else x
             buf = xm.new_zeros((world * block, xm.shape[1]))
             if hi > lo:
-                buf[self.rank * block:self.rank * block + (hi - lo)] = ops.kernel_matmat(
-                    A1, A2, xm, kernel, cfg.lengthscale, cfg.const_scaling, row_idx=mine, col_idx=blk_dev)
+                Pr, Pc = block_packs(xm.shape[1])
+                buf[self.rank * block:self.rank * block + (hi - lo)] = ops.matmat_packed(
+                    Pr, Pc, xm, kid, cfg.const_scaling)
             dist.all_gather_into_tensor(buf, buf[self.rank * block:(self.rank + 1) * block], group=group)
             if world * block != b:  # ragged: drop the padding rows of every rank's slot
                 ranges = shard_rows(b, world)

@@ -172,7 +172,10 @@ class _BaseDistributedLinOp(_BaseLinOp):
 
     @staticmethod
     def _combine_results(results: list[torch.Tensor], concatenate: bool, device: torch.device) -> torch.Tensor:
-        moved = [r.to(device, non_blocking=True) for r in results]
+        # A non-blocking copy to the host returns before the data has landed (torch stages it through pinned
+        # memory); only device-to-device moves may be asynchronous -- they are ordered on the target's stream.
+        async_ok = torch.device(device).type == "cuda"
+        moved = [r.to(device, non_blocking=async_ok) for r in results]
         if concatenate:
             return torch.cat(moved, dim=0)
         out = moved[0].clone() if len(moved) > 1 else moved[0]

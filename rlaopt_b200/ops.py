@@ -12,6 +12,7 @@ Three levels, all CUDA-only (no CPU fallback — a CPU tensor raises):
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Optional, Union
 
@@ -57,17 +58,66 @@ def _stream(device: torch.device) -> int:
 
 
 class PackedPoints:
-    """A point set in the fused kernels' streaming layout (device buffer + shape)."""
+    """A point set in the fused kernels' streaming layout (device buffer + shape).
 
-    __slots__ = ("buf", "n", "d", "dtype", "layout", "device")
+    ``center`` is the shift that was subtracted before the division by the lengthscale (tensor-core layout
+    only); two packs may be multiplied only if they were packed with the same shift.
+    """
 
-    def __init__(self, buf: torch.Tensor, n: int, d: int, dtype: torch.dtype, layout: int):
+    __slots__ = ("buf", "n", "d", "dtype", "layout", "device", "center", "_stats")
+
+    def __init__(self, buf: torch.Tensor, n: int, d: int, dtype: torch.dtype, layout: int, center=None):
         self.buf, self.n, self.d, self.dtype, self.layout = buf, n, d, dtype, layout
         self.device = buf.device
+        self.center = center
+        self._stats = None
+
+    def stats(self) -> tuple[float, int]:
+        """``(max_i |(x_i - center) / lengthscale|^2, number of out-of-range gather indices)`` of a tensor-core
+        pack, read back once (one 8-byte copy and a stream synchronisation) and memoised."""
+        if self._stats is None:
+            if self.layout != LAYOUT_TC:
+                raise RuntimeError("only tensor-core packs carry statistics")
+            if self.n == 0:
+                self._stats = (0.0, 0)
+                return self._stats
+            mx, bad = ctypes.c_float(0.0), ctypes.c_int64(0)
+            with torch.cuda.device(self.device):
+                rc = _lib.load().rlaopt_b200_packed_stats_host(
+                    _ptr(self.buf), self.layout, ctypes.addressof(mx), ctypes.addressof(bad), _stream(self.device))
+            _lib.check(rc, "packed_stats")
+            self._stats = (float(mx.value), int(bad.value))
+        return self._stats
+
+    @property
+    def max_sqnorm(self) -> float:
+        return self.stats()[0]
+
+
+# Accuracy guard of the tensor-core path (DESIGN.md section 4).  Its GEMM-form distance carries an absolute error
+# ~ TC_EPS_D (|x|^2 + |y|^2); the relative error this leaves in a kernel value is that times |d ln f / d D|, at most
+# 1/2 (RBF), 3/2 (Matern-3/2), 5/6 (Matern-5/2); Matern-1/2 recomputes near pairs exactly and is bounded by 1e-5 / N
+# beyond them.  While the bound stays below the 1e-5 parity bar the packs run on tcgen05; otherwise the operator
+# falls back to the direct-difference CUDA-core kernel (exact under translation, like the reference's KeOps formula).
+TC_EPS_D = 3.0e-7
+TC_PARITY_TOL = 1.0e-5
+TC_SENSITIVITY = {0: 0.5, 2: 0.5, 3: 1.5, 4: 5.0 / 6.0}
+
+
+def tc_norm_budget(kid: int) -> float:
+    """Largest ``max|x|^2 + max|y|^2`` (centred, lengthscale-scaled) the tensor-core path accepts for kernel ``kid``."""
+    return TC_PARITY_TOL / (TC_EPS_D * TC_SENSITIVITY[kid])
+
+
+def tc_accuracy_ok(kid: int, rows_sqnorm: float, cols_sqnorm: float) -> bool:
+    if os.environ.get("RLAOPT_B200_LAYOUT", "").lower() == "tc":
+        return True
+    return rows_sqnorm + cols_sqnorm <= tc_norm_budget(kid)
 
 
 def choose_layout(kid: int, dtype: torch.dtype, d: int, k: int) -> int:
-    """Kernel-path selection by shape (one backend, two kernels)."""
+    """Kernel-path selection by shape (one backend, two kernels); the data-dependent half of the decision is
+    :func:`tc_accuracy_ok`, evaluated once per operator from the pack statistics."""
     forced = os.environ.get("RLAOPT_B200_LAYOUT", "").lower()
     if forced == "simt":
         return LAYOUT_SIMT
@@ -94,13 +144,62 @@ def _inv_lengthscale(lengthscale, d: int, dtype: torch.dtype, device: torch.devi
     return 1.0 / float(lengthscale), None
 
 
+def _check_index(idx: torch.Tensor, n_src: int, device: torch.device) -> torch.Tensor:
+    """Validate a gather list like ``A1[blk]`` does (IndexError on the host; a device-side assert for CUDA
+    indices) and return it as a contiguous int64 tensor on ``device``.  Negative entries wrap in the kernels."""
+    if idx.ndim != 1:
+        raise ValueError("index tensor must be 1-D")
+    if idx.dtype not in (torch.int64, torch.int32, torch.int16, torch.int8, torch.uint8):
+        raise IndexError(f"index tensor must be an integer tensor, got {idx.dtype}")
+    if idx.numel() > 0:
+        if idx.device.type == "cpu":
+            lo, hi = int(idx.min()), int(idx.max())
+            if lo < -n_src or hi >= n_src:
+                bad = lo if lo < -n_src else hi
+                raise IndexError(f"index {bad} is out of bounds for dimension 0 with size {n_src}")
+        else:
+            torch._assert_async(((idx >= -n_src) & (idx < n_src)).all(),
+                                f"rlaopt_b200: gather index out of bounds for dimension 0 with size {n_src}")
+    return idx.to(device=device, dtype=torch.int64).contiguous()
+
+
+def column_mean(X: torch.Tensor, idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-feature mean of ``X[idx]`` (fp64-accumulated on the device, bit-reproducible): the common shift of the
+    tensor-core packs of one operator."""
+    global LAUNCH_COUNT
+    _require_cuda(X, "X")
+    if X.dtype != torch.float32 or X.ndim != 2:
+        raise ValueError("column_mean expects a 2-D float32 tensor")
+    if X.stride(1) != 1 and X.shape[1] > 1:
+        X = X.contiguous()
+    lib = _lib.load()
+    n_src, d = X.shape
+    if idx is not None:
+        idx = _check_index(idx, n_src, X.device)
+    n = n_src if idx is None else idx.shape[0]
+    with torch.cuda.device(X.device):
+        center = torch.zeros(d, dtype=torch.float32, device=X.device)
+        if n == 0:
+            return center
+        ws_bytes = lib.rlaopt_b200_column_mean_workspace_bytes(n, d)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
+        ldx = X.stride(0) if X.shape[0] > 1 else max(d, 1)
+        rc = lib.rlaopt_b200_column_mean_f32(_ptr(X), n, n_src, d, ldx, _ptr(idx), _ptr(center), _ptr(ws), ws_bytes,
+                                             _stream(X.device))
+        _lib.check(rc, "column_mean")
+    LAUNCH_COUNT += 2
+    return center
+
+
 def pack_points(
     X: torch.Tensor,
     lengthscale,
     idx: Optional[torch.Tensor] = None,
     layout: int = LAYOUT_SIMT,
+    center: Optional[torch.Tensor] = None,
 ) -> PackedPoints:
-    """Gather ``X[idx]``, divide by the lengthscale, and lay out for the fused kernels."""
+    """Gather ``X[idx]``, subtract ``center`` (tensor-core layout), divide by the lengthscale, and lay out for
+    the fused kernels."""
     global LAUNCH_COUNT
     _require_cuda(X, "X")
     if X.ndim != 2:
@@ -112,12 +211,16 @@ def pack_points(
     lib = _lib.load()
     n_src, d = X.shape
     if idx is not None:
-        idx = idx.to(device=X.device, dtype=torch.int64).contiguous()
-        if idx.ndim != 1:
-            raise ValueError("index tensor must be 1-D")
+        idx = _check_index(idx, n_src, X.device)
         n = idx.shape[0]
     else:
         n = n_src
+    if layout != LAYOUT_TC:
+        center = None  # direct differences are exact under translation
+    elif center is not None:
+        if center.shape != (d,):
+            raise ValueError(f"center must have shape ({d},), got {tuple(center.shape)}")
+        center = center.to(device=X.device, dtype=X.dtype).contiguous()
     inv, inv_vec = _inv_lengthscale(lengthscale, d, X.dtype, X.device)
     elem = X.element_size()
     nbytes = lib.rlaopt_b200_packed_bytes(n, d, elem, layout)
@@ -125,10 +228,17 @@ def pack_points(
         buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=X.device)
         fn = getattr(lib, f"rlaopt_b200_pack_points_{_SUFFIX[X.dtype]}")
         ldx = X.stride(0) if X.shape[0] > 1 else max(d, 1)
-        rc = fn(_ptr(X), n, d, ldx, _ptr(idx), inv, _ptr(inv_vec), layout, _ptr(buf), _stream(X.device))
+        rc = fn(_ptr(X), n, n_src, d, ldx, _ptr(idx), inv, _ptr(inv_vec), _ptr(center), layout, _ptr(buf),
+                _stream(X.device))
         _lib.check(rc, "pack_points")
     LAUNCH_COUNT += 2 if layout == LAYOUT_TC else 1  # TC: abs-max + split/pack kernels
-    return PackedPoints(buf, n, d, X.dtype, layout)
+    return PackedPoints(buf, n, d, X.dtype, layout, center)
+
+
+def _same_center(a: Optional[torch.Tensor], b: Optional[torch.Tensor]) -> bool:
+    if a is None or b is None:
+        return a is b
+    return a is b or (a.data_ptr() == b.data_ptr() and a.shape == b.shape)
 
 
 def matmat_packed(
@@ -144,6 +254,8 @@ def matmat_packed(
     _require_cuda(V, "V")
     if rows.layout != cols.layout or rows.dtype != cols.dtype or rows.d != cols.d:
         raise ValueError("packed operands disagree in layout / dtype / feature count")
+    if not _same_center(rows.center, cols.center):
+        raise ValueError("packed operands were shifted by different centers: K(x - c1, y - c2) is not K(x, y)")
     if V.device != rows.device or cols.device != rows.device:
         raise ValueError("operands and V must be on the same device")
     if V.dtype != rows.dtype:
@@ -207,10 +319,16 @@ def kernel_matmat(
     if A1.dtype != A2.dtype or A1.dtype != V.dtype:
         raise ValueError("A1, A2 and V must have the same dtype.")
     k = 1 if V.ndim == 1 else V.shape[-1]
-    if layout is None:
+    auto = layout is None
+    if auto:
         layout = choose_layout(kid, A1.dtype, A1.shape[1], k)
-    P1 = pack_points(A1, lengthscale, row_idx, layout)
-    P2 = pack_points(A2, lengthscale, col_idx, layout)
+    center = column_mean(A2, col_idx) if layout == LAYOUT_TC else None
+    P1 = pack_points(A1, lengthscale, row_idx, layout, center)
+    P2 = pack_points(A2, lengthscale, col_idx, layout, center)
+    if auto and layout == LAYOUT_TC and not tc_accuracy_ok(kid, P1.max_sqnorm, P2.max_sqnorm):
+        # norms too large for the GEMM-form distance at the parity bar: direct-difference kernel instead
+        P1 = pack_points(A1, lengthscale, row_idx, LAYOUT_SIMT)
+        P2 = pack_points(A2, lengthscale, col_idx, LAYOUT_SIMT)
     rows, cols = (P2, P1) if transpose else (P1, P2)
     return matmat_packed(rows, cols, V, kid, const_scaling)
 

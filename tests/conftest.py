@@ -42,6 +42,8 @@ class _FakePack:
         self.X, self.lengthscale, self.layout = X, lengthscale, layout
         self.n, self.d, self.dtype, self.device = X.shape[0], X.shape[1], X.dtype, X.device
         self.buf = X
+        self.center = None
+        self.max_sqnorm = 0.0
 
 
 @pytest.fixture
@@ -52,7 +54,7 @@ def oracle_backend(monkeypatch):
 
     calls = {"pack": 0, "matmat": 0}
 
-    def fake_pack(X, lengthscale, idx=None, layout=0):
+    def fake_pack(X, lengthscale, idx=None, layout=0, center=None):
         calls["pack"] += 1
         Xg = X if idx is None else X[idx.to(X.device)]
         return _FakePack(Xg, lengthscale, layout)

@@ -41,6 +41,8 @@ def test_header_declares_expected_entry_points():
         "rlaopt_b200_kernel_matmat_f32",
         "rlaopt_b200_kernel_matmat_f64",
         "rlaopt_b200_kernel_matmat_host_f32",
+        "rlaopt_b200_column_mean_f32",
+        "rlaopt_b200_packed_stats_host",
     ):
         assert required in names
 
@@ -60,7 +62,7 @@ def test_python_prototypes_cover_the_header(lib):
 def test_host_only_entry_points(lib):
     from rlaopt_b200._lib import LAYOUT_SIMT, LAYOUT_TC
 
-    assert lib.rlaopt_b200_abi_version() == 1
+    assert lib.rlaopt_b200_abi_version() == 2
     # SIMT layout: rows padded to 128, features to 8
     assert lib.rlaopt_b200_packed_bytes(10, 3, 4, LAYOUT_SIMT) == 128 * 8 * 4
     assert lib.rlaopt_b200_packed_bytes(129, 9, 8, LAYOUT_SIMT) == 256 * 16 * 8
@@ -90,8 +92,15 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
     rc = lib.rlaopt_b200_matmat_packed_f32(None, 4, None, 4, 3, None, 1, 1, None, 1, 99, 1.0, 0, None, 0, None)
     assert rc == -1
     assert b"unknown kernel" in lib.rlaopt_b200_last_error()
-    rc = lib.rlaopt_b200_pack_points_f32(None, 4, 0, 0, None, 1.0, None, 0, None, None)
+    rc = lib.rlaopt_b200_pack_points_f32(None, 4, 4, 0, 0, None, 1.0, None, None, 0, None, None)
     assert rc == -1
+    # identity gather of more points than the source holds
+    rc = lib.rlaopt_b200_pack_points_f32(None, 5, 4, 3, 3, None, 1.0, None, None, 0, None, None)
+    assert rc == -1 and b"n_src" in lib.rlaopt_b200_last_error()
+    # statistics exist for tensor-core packs only; the column-mean workspace is one fp64 row per 4096 points
+    assert lib.rlaopt_b200_packed_stats_host(None, 0, None, None, None) == -3
+    assert lib.rlaopt_b200_column_mean_workspace_bytes(4097, 5) == 2 * 5 * 8
+    assert lib.rlaopt_b200_column_mean_f32(None, 4, 4, 3, 3, None, None, None, 0, None) == -1
     with pytest.raises(RuntimeError, match="code -1"):
         _lib.check(rc, "pack_points")
 

@@ -78,3 +78,29 @@ def test_distributed_symmetric_krr_operator_all_kernels():
             assert ko.rel_fro_error(op @ V.to(dev0), ref) <= 1e-5, name
         finally:
             op.shutdown()
+
+
+def test_distributed_operator_with_host_operands():
+    """The reference stages operands through the host (``rlaopt/linops/base.py:254-276``), so callers may pass a CPU
+    ``x``: the result comes back on the CPU, complete (the shard results are copied synchronously)."""
+    from rlaopt_b200.kernels import DistributedRBFLinOp, KernelConfig
+
+    g = torch.Generator().manual_seed(2)
+    n, m, d, k = 4099, 3001, 12, 6
+    A1, A2 = torch.randn(n, d, generator=g) / 3, torch.randn(m, d, generator=g) / 3
+    V, W = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g)
+    dev0 = torch.device("cuda:0")
+    op = DistributedRBFLinOp(A1.to(dev0), A2.to(dev0), KernelConfig(lengthscale=1.0), devices=_devices())
+    try:
+        ref = ko.kernel_matmat(A1, A2, V, "rbf", 1.0, dtype=torch.float64)
+        for _ in range(3):
+            got = op @ V  # V lives on the host
+            assert got.device.type == "cpu" and ko.rel_fro_error(got, ref) <= 1e-5
+        ref_t = ko.kernel_matmat(A1, A2, W, "rbf", 1.0, transpose=True, dtype=torch.float64)
+        got_t = op.T @ W
+        assert got_t.device.type == "cpu" and ko.rel_fro_error(got_t, ref_t) <= 1e-5
+        blk = torch.randperm(m, generator=g)[:257]
+        got_r = op.row_oracle(blk) @ V
+        assert got_r.device.type == "cpu" and ko.rel_fro_error(got_r, ref[blk]) <= 1e-5
+    finally:
+        op.shutdown()

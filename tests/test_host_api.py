@@ -218,3 +218,62 @@ def test_shared_operand_is_packed_once(mats, oracle_backend):
     K @ torch.randn(10, dtype=A1.dtype)
     torch.randn(10, dtype=A1.dtype) @ K
     assert oracle_backend["pack"] == 1
+
+
+def test_gather_index_validation_is_host_logic():
+    """``A1[blk]`` semantics for the oracles' index lists (ADVICE r1): range errors raise IndexError before any
+    kernel is launched; negative entries are legal (they wrap in the pack kernels)."""
+    import pytest
+    import torch
+
+    from rlaopt_b200 import ops
+
+    cpu = torch.device("cpu")
+    out = ops._check_index(torch.tensor([0, -1, 4, -5]), 5, cpu)
+    assert out.dtype == torch.int64 and out.tolist() == [0, -1, 4, -5]
+    assert ops._check_index(torch.tensor([], dtype=torch.int64), 5, cpu).numel() == 0
+    for bad in ([5], [-6], [0, 1, 99]):
+        with pytest.raises(IndexError, match="out of bounds"):
+            ops._check_index(torch.tensor(bad), 5, cpu)
+    with pytest.raises(ValueError):
+        ops._check_index(torch.zeros(2, 2, dtype=torch.int64), 5, cpu)
+    with pytest.raises(IndexError):
+        ops._check_index(torch.tensor([0.0, 1.0]), 5, cpu)
+
+
+def test_pack_cache_tracks_in_place_edits(oracle_backend):
+    """The pack cache is keyed on the in-place versions of A1, A2 and the lengthscale tensor (VERDICT r1 weak #9)."""
+    import torch
+
+    from rlaopt_b200.kernels import KernelConfig, RBFLinOp
+
+    X = torch.randn(20, 3)
+    ls = torch.ones(3)
+    op = RBFLinOp(X, X, KernelConfig(lengthscale=ls))
+    v = torch.randn(20)
+    op @ v
+    op @ v
+    assert oracle_backend["pack"] == 1  # one shared pack, reused
+    X.mul_(2.0)
+    op @ v
+    assert oracle_backend["pack"] == 2  # data edited in place: repacked
+    ls.add_(1.0)
+    op @ v
+    assert oracle_backend["pack"] == 3  # lengthscale edited in place: repacked
+    blk = torch.tensor([1, 2, 3])
+    ro = op.row_oracle(blk)
+    ro @ v
+    ro @ v
+    packs = oracle_backend["pack"]
+    X.add_(1.0)
+    ro @ v
+    assert oracle_backend["pack"] == packs + 2  # block pack and column pack both rebuilt
+
+
+def test_tc_accuracy_budget():
+    from rlaopt_b200 import ops
+
+    assert ops.tc_accuracy_ok(ops.KERNEL_IDS["rbf"], 30.0, 30.0)
+    assert not ops.tc_accuracy_ok(ops.KERNEL_IDS["rbf"], 40.0, 40.0)
+    assert ops.tc_norm_budget(ops.KERNEL_IDS["matern32"]) < ops.tc_norm_budget(ops.KERNEL_IDS["matern52"]) \
+        < ops.tc_norm_budget(ops.KERNEL_IDS["rbf"])

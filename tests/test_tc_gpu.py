@@ -317,5 +317,7 @@ def test_register_contraction_long_positive_sum_and_tiny_values(dev):
     assert ko.rel_fro_error(got, ref) <= 1e-6
     far = A1 + 4.2  # squared distances ~ 140: K ~ 1e-30
     ref = ko.kernel_matmat_gemm_form(far, A2[:5000], V[:5000], "rbf", 1.0, dtype=torch.float64)
-    got = kernel_matmat(far.to(dev), A2[:5000].to(dev), V[:5000].to(dev), "rbf", 1.0, layout=LAYOUT_TC)
-    assert ko.rel_fro_error(got, ref) <= 2e-4  # eps (|x|^2 + |y|^2) of the GEMM-form distance times log-slope; values ~1e-30
+    # |x|^2 ~ 140 is beyond the tensor-core accuracy budget (ops.tc_accuracy_ok): with the automatic layout the
+    # guard sends these rows to the direct-difference kernel and the 1e-5 bar holds (values ~1e-30)
+    got = kernel_matmat(far.to(dev), A2[:5000].to(dev), V[:5000].to(dev), "rbf", 1.0)
+    assert ko.rel_fro_error(got, ref) <= 1e-5
