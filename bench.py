@@ -148,10 +148,78 @@ def cpu_baseline(kernel: str, X: torch.Tensor, V: torch.Tensor, budget_s: float 
     }
 
 
+def _use_all_host_cores() -> int:
+    """torchrun pins OMP_NUM_THREADS=1 in every rank's environment; the reference arm is a CPU measurement and uses
+    every core this process may run on, whatever launched it."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    os.environ.pop("OMP_NUM_THREADS", None)
+    os.environ.pop("MKL_NUM_THREADS", None)
+    torch.set_num_threads(cores)
+    return cores
+
+
+def _reference_solver_stack():
+    """The UNMODIFIED reference installed in baseline/_ref by oracle/build_ref.py (everything but rlaopt.kernels,
+    which needs PyKeOps), or None."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "rlaopt", "__init__.py")):
+        return None
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import rlaopt  # noqa: F401  the reference
+        from rlaopt.linops import SymmetricLinOp
+        from rlaopt.models import LinSys
+        from rlaopt.preconditioners import NystromConfig
+        from rlaopt.solvers import PCGConfig
+    except Exception as err:  # an unusable install is reported, not hidden
+        print(f"[bench] reference install in baseline/_ref is not importable: {err!r}", file=sys.stderr)
+        return None
+    return {"SymmetricLinOp": SymmetricLinOp, "LinSys": LinSys, "NystromConfig": NystromConfig, "PCGConfig": PCGConfig}
+
+
+def reference_krr_pcg() -> dict:
+    """BASELINE configs[0] on the CPU with the reference's OWN LinSys.solve + PCG + Nystrom (baseline/_ref) over the
+    oracle's torch kernel operator (the reference's kernel operator itself needs PyKeOps)."""
+    from oracle import kernel_oracle as ko
+
+    stack = _reference_solver_stack()
+    cpu = torch.device("cpu")
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(C1["n"], C1["d"], generator=g) / C1["d"] ** 0.5
+    B = torch.randn(C1["n"], C1["k"], generator=g)
+    mm = lambda Vc: ko.kernel_matmat_gemm_form(X, X, Vc, "rbf", 1.0)
+    if stack is None:
+        from rlaopt_b200.linops import SymmetricLinOp
+
+        out = krr_pcg_solve(cpu, lambda Xc: SymmetricLinOp(cpu, torch.Size((C1["n"], C1["n"])), mm, mm,
+                                                           dtype=torch.float32), reps=0)
+        out["solver_stack"] = "port (baseline/_ref missing: this package's solvers on the CPU)"
+        return out
+    A = stack["SymmetricLinOp"](cpu, torch.Size((C1["n"], C1["n"])), mm, mm, dtype=torch.float32)
+    torch.manual_seed(1)
+    t0 = time.perf_counter()
+    system = stack["LinSys"](A, B, reg=C1["reg"])
+    cfg = stack["PCGConfig"](device=cpu, max_iters=C1["max_iters"], rtol=C1["rtol"],
+                             precond_config=stack["NystromConfig"](rank=C1["rank"], rho=C1["reg"], sketch="gauss"))
+    W, log = system.solve(cfg, torch.zeros(C1["n"], C1["k"]), callback_freq=1)
+    dt = time.perf_counter() - t0
+    iters = max(log)
+    rel = float(log[iters]["metrics"]["internal_metrics"]["rel_res"].max())
+    return {"seconds": dt, "iterations": iters, "rel_res": rel, "unit": "s",
+            "config": "RBF KRR n=20000 d=8 k=1, Nystrom rank 200 (gauss), reg=1.0, rtol=1e-4, fp32, callback_freq=1",
+            "solver_stack": "reference (unmodified rlaopt.models / solvers / preconditioners from baseline/_ref) over "
+                            "the oracle's CPU torch kernel operator"}
+
+
 def run_reference(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    cores = _use_all_host_cores()
     kernel, n, d, k = WORKLOADS[args.workload]
     X, V = make_data(kernel, n, d, k)
     vals, base = [], None
@@ -160,7 +228,6 @@ def run_reference(args) -> int:
         if i >= args.warmup:
             vals.append(base)
     value = statistics.mean(b["value"] for b in vals)
-    ms = statistics.mean(b["seconds"] for b in vals) * 1e3
     line = {
         "impl": "reference",
         "metric": "kernel_matmat_gentries_per_s",
@@ -169,7 +236,9 @@ def run_reference(args) -> int:
         "n_gpus": args.gpus,
         "steps": args.steps,
         "warmup": args.warmup,
-        "ms_per_step": ms,
+        # time one full step of the stated config would take at the sampled rate (a step here is a bounded row sample)
+        "ms_per_step": n * n / (value * 1e9) * 1e3,
+        "ms_per_sample": statistics.mean(b["seconds"] for b in vals) * 1e3,
         "higher_is_better": True,
         "scaling": "strong",
         "vs_baseline": None,
@@ -180,19 +249,9 @@ def run_reference(args) -> int:
         "e2e": {"value": value, "unit": "Gentries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    assert line["cpu_baseline"]["cores"] == cores
     if not args.no_krr:
-        from oracle import kernel_oracle as ko
-        from rlaopt_b200.linops import SymmetricLinOp
-
-        cpu = torch.device("cpu")
-
-        def oracle_op(Xc):
-            nn = Xc.shape[0]
-            mm = lambda Vc: ko.kernel_matmat_gemm_form(Xc, Xc, Vc, "rbf", 1.0)
-            return SymmetricLinOp(cpu, torch.Size((nn, nn)), mm, mm, dtype=torch.float32)
-
-        line["krr_pcg"] = krr_pcg_solve(cpu, oracle_op, reps=0)
-        line["krr_pcg"]["note"] = "reference solver arithmetic (PCG + Nystrom) on the CPU over the oracle's torch kernel operator"
+        line["krr_pcg"] = reference_krr_pcg()
     print(json.dumps(line), flush=True)
     return 0
 
@@ -269,6 +328,99 @@ def single_rhs_matvec(device) -> dict:
     return {"value": b * n / ms / 1e6, "unit": "Gentries/s", "ms": ms,
             "config": f"RBF K(X[:{b}], X) @ v, n={n}, d={d}, k=1, fp32 (V re-packed per call, X packs cached)",
             "checksum_abs_sum": float(y.double().abs().sum().item())}
+
+
+# ----------------------------------------------------------------------------- secondary workloads (1 GPU)
+# Row samples of the other BASELINE configs, K(X[:r], X) @ V at the full column count m, so that every default run
+# of bench.py (the driver's) times them on the final binary.  r is a whole number of CTA waves of that kernel.
+SECONDARY = {
+    # name: (kernel, m, d, k, rows)
+    "c3_laplace": ("laplace", 4_000_000, 32, 16, 113_664),    # 888 row tiles = 2 waves of 3 CTAs x 148 SMs
+    "c3_matern52": ("matern52", 4_000_000, 32, 16, 265_216),  # 2072 row tiles = 14 waves of 148 CTAs
+    "c5_sketch": ("rbf", 2_000_000, 64, 1000, 94_720),        # 740 row tiles = 5 waves (Nystrom sketch K @ Omega)
+}
+
+
+def binding_roofline(kernel: str, d: int, k: int, entries: float, seconds: float, layout_tc: bool, peaks: dict,
+                     sm_mhz, sustained: bool = False) -> dict:
+    """Roofline of the BINDING pipe ("report the binding one"):
+
+    * tensor   -- tcgen05 path: 6d + 6k fp16 flop per entry (3-product hi/lo split of X.Y^T and P.V) against the
+                  measured cuBLAS bf16 rate;
+    * mufu     -- tcgen05 path with little tensor work per entry: 1 (RBF) or 2 (Matern: sqrt + ex2) special-function
+                  ops per entry against 148 SMs x 16 lanes x clock;
+    * fp32     -- CUDA-core path: 2d + k lane-ops per entry (FADD + FFMA per feature, FFMA per column of V) against
+                  148 SMs x 128 lanes x clock.
+    The clock-bound pipes are quoted against the maximum SM clock (conservative) and against the clock sampled
+    during the run."""
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    cands = []
+    if layout_tc:
+        # a kernel timed alone for about a second: burst figure; inside a long loop of steps: sustained (B200_PROFILING.md)
+        key = "bf16_tflops_sustained" if sustained else "bf16_tflops"
+        bf16 = float(peaks.get(key, peaks.get("bf16_tflops", 1590.0))) * 1e12
+        cands.append(("tensor", (6 * d + 6 * k) * entries / seconds, bf16, "fp16 tensor flop/s",
+                      f"{peaks['_source']} cuBLAS bf16 {'sustained' if sustained else 'burst'} {bf16 / 1e12:.0f} TFLOP/s; "
+                      "tensor work 6d+6k flop per entry"))
+        mufu_ops = 1 if kernel == "rbf" else 2
+        cands.append(("mufu", mufu_ops * entries / seconds, SM_COUNT_B200 * 16 * sm_max * 1e6, "special-function op/s",
+                      f"148 SMs x 16 MUFU lanes x {sm_max:.0f} MHz; {mufu_ops} op per entry"))
+    else:
+        cands.append(("fp32", (2 * d + k) * entries / seconds, SM_COUNT_B200 * FP32_LANES_PER_SM * sm_max * 1e6,
+                      "fp32 lane-op/s", f"148 SMs x 128 FP32 lanes x {sm_max:.0f} MHz; 2d+k lane-ops per entry"))
+    bound, achieved, peak, unit, note = max(cands, key=lambda c: c[1] / c[2])
+    out = {"bound": bound, "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T" + unit, "frac": achieved / peak,
+           "peak_note": note, "flops_per_entry": 2 * d + 2 * k,
+           "algorithmic_tflops": (2 * d + 2 * k) * entries / seconds / 1e12}
+    if bound != "tensor" and sm_mhz:
+        out["frac_at_sampled_clock"] = achieved / (peak * float(sm_mhz) / sm_max)
+        out["sampled_sm_mhz"] = sm_mhz
+    return out
+
+
+def secondary_leg(name: str, dev, peaks: dict, gpu_index: int, warm: int = 2, steps: int = 4) -> dict:
+    from rlaopt_b200 import _lib, ops
+    from rlaopt_b200.kernels import KernelConfig
+    from rlaopt_b200.kernels.base import _KernelLinOp
+
+    kernel, m, d, k, rows = SECONDARY[name]
+    g = torch.Generator(device=dev).manual_seed(0)  # generated on the device: 2 G random numbers for Omega
+    X = torch.randn(m, d, generator=g, device=dev) / d**0.5
+    V = torch.randn(m, k, generator=g, device=dev)
+    if name == "c5_sketch":
+        V /= k**0.5  # Gaussian sketch Omega / sqrt(rank), rlaopt/sketches/gauss.py:46-48
+    op = _KernelLinOp(X[:rows], X, KernelConfig(lengthscale=1.0), _kernel_key=kernel)
+    layout = op._layout_for(V)
+    for _ in range(warm):
+        Y = op @ V
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(gpu_index)
+    sampler.start()
+    launches0 = ops.LAUNCH_COUNT
+    ts = []
+    for _ in range(steps):
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        Y = op @ V
+        e.record()
+        torch.cuda.synchronize(dev)
+        ts.append(a.elapsed_time(e))
+    clocks = sampler.stop()
+    ms = statistics.mean(ts)
+    entries = float(rows) * m
+    out = {
+        "value": entries / ms / 1e6, "unit": "Gentries/s", "ms": ms, "steps": steps,
+        "config": f"{kernel} K(X[:{rows}], X) @ V, m={m}, d={d}, k={k}, fp32, lengthscale=1.0 "
+                  f"(row sample of the BASELINE config at the full column count; X packs cached, V packed per call)",
+        "kernel_path": "tcgen05" if layout == _lib.LAYOUT_TC else "cuda-core",
+        "roofline": binding_roofline(kernel, d, k, entries, ms * 1e-3, layout == _lib.LAYOUT_TC, peaks, clocks.get("sm_mhz")),
+        "clocks": clocks,
+        "gpu_launches": ops.LAUNCH_COUNT - launches0,
+        "checksum_abs_sum": float(Y.double().abs().sum().item()),
+    }
+    del op, X, V, Y
+    torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------- ours
@@ -414,6 +566,15 @@ def run_ours(args) -> int:
         "flops_per_entry": 2 * d + 2 * k,
         "hbm_algorithmic_gb": 4 * (n * d + n * k + rows_per_rank * k) / 1e9,
     }
+    if args.workload not in ("c2", "small"):
+        # the other workloads are not bound by the algorithmic-flop rate of one pipe: quote the binding pipe
+        extra = binding_roofline(kernel, d, k, float(rows_per_rank) * n, kernel_ms * 1e-3, layout == _lib.LAYOUT_TC,
+                                 peaks, clocks.get("sm_mhz") if clocks else None, sustained=True)
+        roofline.update({kk: extra[kk] for kk in ("bound", "achieved", "peak", "unit", "frac", "peak_note")})
+        roofline.pop("frac_vs_burst", None)
+        for kk in ("frac_at_sampled_clock", "sampled_sm_mhz", "algorithmic_tflops"):
+            if kk in extra:
+                roofline[kk] = extra[kk]
 
     line = {
         "metric": "kernel_matmat_gentries_per_s",
@@ -453,6 +614,9 @@ def run_ours(args) -> int:
         torch.cuda.empty_cache()
         line["krr_pcg"] = krr_pcg_solve(dev, lambda Xd: RBFLinOp(Xd, Xd, cfg), reps=2)
         line["single_rhs_matvec"] = single_rhs_matvec(dev)
+    if world == 1 and not args.no_secondary and args.workload == "c2":
+        for name in SECONDARY:
+            line[name] = secondary_leg(name, dev, peaks, local_rank)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -470,6 +634,8 @@ def main() -> int:
     ap.add_argument("--ref-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-krr", action="store_true", help="skip the secondary KRR PCG solve (BASELINE configs[0])")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the row-sampled C3 (Laplace, Matern-5/2) and C5 (sketch) legs of the default run")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
