@@ -128,6 +128,70 @@ int rlaopt_b200_matmat_packed_f64(const void* rows_packed, int64_t n, const void
                                   void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Fused output stage: the same product with the callers' next passes folded in,
+ *
+ *     Y[i,:]     = alpha * const_scaling * (K V)[i,:] + beta * addend[ai(i),:] + gamma * rhs[ri(i),:]
+ *     gram_out   = gram_lhs^T Y     (gram_cols x k, optional; k, gram_cols <= 64)
+ *     sqnorm_out = column sums of Y^2 (k, optional; k <= 64)
+ *
+ * with ai(i) = addend_idx[i] (or i when NULL; negative entries wrap, out-of-range rows contribute 0), same for rhs.
+ * One pass, no n x k temporary (Y may be NULL when only the reductions are wanted); the reductions are
+ * deterministic (fixed summation order, fp64 across blocks).  Replaces
+ *     A @ P + reg * P   and   P^T (A P)                 rlaopt/solvers/pcg.py:58-61   (beta = reg, addend = gram_lhs = P)
+ *     B - (A @ W + reg * W), its column norms           rlaopt/models/linsys.py:96-99, rlaopt/solvers/pcg.py:33
+ *                                                       (alpha = -1, beta = -reg, addend = W, gamma = 1, rhs = B)
+ *     A_row_oracle(blk) @ Y + reg * Y[blk] - B[blk]     rlaopt/solvers/sap.py:113-127 (addend_idx = rhs_idx = blk)
+ * Workspace: rlaopt_b200_matmat_fused_workspace_bytes.
+ * ------------------------------------------------------------------------- */
+typedef struct rlaopt_b200_epilogue_f32 {
+    float alpha;
+    float beta;
+    const float* addend;       /* NULL = no term */
+    int64_t ld_addend, addend_rows;
+    const int64_t* addend_idx;
+    float gamma;
+    const float* rhs;          /* NULL = no term */
+    int64_t ld_rhs, rhs_rows;
+    const int64_t* rhs_idx;
+    const float* gram_lhs;     /* [n][gram_cols], NULL = no Gram */
+    int64_t ld_gram_lhs;
+    int64_t gram_cols;
+    float* gram_out;           /* [gram_cols][k], row-major */
+    float* sqnorm_out;         /* [k], NULL = not wanted */
+} rlaopt_b200_epilogue_f32;
+
+typedef struct rlaopt_b200_epilogue_f64 {
+    double alpha;
+    double beta;
+    const double* addend;
+    int64_t ld_addend, addend_rows;
+    const int64_t* addend_idx;
+    double gamma;
+    const double* rhs;
+    int64_t ld_rhs, rhs_rows;
+    const int64_t* rhs_idx;
+    const double* gram_lhs;
+    int64_t ld_gram_lhs;
+    int64_t gram_cols;
+    double* gram_out;
+    double* sqnorm_out;
+} rlaopt_b200_epilogue_f64;
+
+size_t rlaopt_b200_matmat_fused_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int elem_bytes, int layout,
+                                                int64_t gram_cols, int want_sqnorm);
+
+int rlaopt_b200_matmat_packed_fused_f32(const void* rows_packed, int64_t n, const void* cols_packed, int64_t m,
+                                        int64_t d, const float* V, int64_t k, int64_t ldv, float* Y, int64_t ldy,
+                                        int kernel_id, float const_scaling, int layout,
+                                        const rlaopt_b200_epilogue_f32* epilogue, void* workspace,
+                                        size_t workspace_bytes, void* stream);
+int rlaopt_b200_matmat_packed_fused_f64(const void* rows_packed, int64_t n, const void* cols_packed, int64_t m,
+                                        int64_t d, const double* V, int64_t k, int64_t ldv, double* Y, int64_t ldy,
+                                        int kernel_id, double const_scaling, int layout,
+                                        const rlaopt_b200_epilogue_f64* epilogue, void* workspace,
+                                        size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
  * One-shot entry: pack both operands into `workspace`, then the fused matmat.
  *   forward   (transpose = 0): Y[n'][k] = c * K(A1[row_idx], A2[col_idx])   @ V[m'][k]
  *   transpose (transpose = 1): Y[m'][k] = c * K(A1[row_idx], A2[col_idx])^T @ V[n'][k]

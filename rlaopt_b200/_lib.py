@@ -18,6 +18,26 @@ LIB_PATH = os.environ.get("RLAOPT_B200_LIB") or os.path.join(_HERE, "csrc", "lib
 LAYOUT_SIMT = 0
 LAYOUT_TC = 1
 
+
+def _epilogue_struct(real):
+    """ctypes mirror of ``rlaopt_b200_epilogue_f32 / _f64`` (include/rlaopt_b200.h)."""
+
+    class Epilogue(ctypes.Structure):
+        _fields_ = [
+            ("alpha", real), ("beta", real),
+            ("addend", c_void_p), ("ld_addend", c_int64), ("addend_rows", c_int64), ("addend_idx", c_void_p),
+            ("gamma", real),
+            ("rhs", c_void_p), ("ld_rhs", c_int64), ("rhs_rows", c_int64), ("rhs_idx", c_void_p),
+            ("gram_lhs", c_void_p), ("ld_gram_lhs", c_int64), ("gram_cols", c_int64), ("gram_out", c_void_p),
+            ("sqnorm_out", c_void_p),
+        ]
+
+    return Epilogue
+
+
+EpilogueF32 = _epilogue_struct(c_float)
+EpilogueF64 = _epilogue_struct(c_double)
+
 _lib = None
 
 # name -> (restype, argtypes); mirrors include/rlaopt_b200.h one to one
@@ -52,6 +72,18 @@ PROTOTYPES = {
         c_int,
         [c_void_p, c_int64, c_void_p, c_int64, c_int64, _f64p, c_int64, c_int64, _f64p, c_int64, c_int, c_double,
          c_int, c_void_p, c_size_t, c_void_p],
+    ),
+    "rlaopt_b200_matmat_fused_workspace_bytes": (
+        c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int64, c_int]),
+    "rlaopt_b200_matmat_packed_fused_f32": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, _f32p, c_int64, c_int64, _f32p, c_int64, c_int, c_float,
+         c_int, c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
+    "rlaopt_b200_matmat_packed_fused_f64": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, _f64p, c_int64, c_int64, _f64p, c_int64, c_int, c_double,
+         c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
     "rlaopt_b200_kernel_matmat_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int, c_int]),
     "rlaopt_b200_kernel_matmat_f32": (

@@ -90,24 +90,102 @@ size_t matmat_workspace_t(int64_t n, int64_t m, int64_t d, int64_t k, int layout
     return 0;
 }
 
+// workspace of the fused form: [main kernel workspace incl. the kept partial sums | reduction partials]
+template <typename T>
+size_t fused_main_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int layout) {
+    if (layout == RLAOPT_B200_LAYOUT_SIMT) return align256(kmm::simt_workspace_bytes<T>(n, m, k, sm_count(), true));
+    if (layout == RLAOPT_B200_LAYOUT_TC && sizeof(T) == 4)
+        return align256(kmm::tc_workspace_bytes(n, m, d, k, sm_count(), true));
+    return 0;
+}
+
+template <typename T>
+size_t fused_workspace_t(int64_t n, int64_t m, int64_t d, int64_t k, int layout, int64_t gram_cols, int want_sqnorm) {
+    if (n <= 0 || k <= 0) return 0;
+    const size_t main_bytes = m > 0 ? fused_main_bytes<T>(n, m, d, k, layout) : 0;
+    return main_bytes + align256(kmm::fuse_workspace_bytes<T>(n, k, gram_cols, want_sqnorm));
+}
+
 template <typename T>
 int matmat_packed_t(const void* rows, int64_t n, const void* cols, int64_t m, int64_t d, const T* V, int64_t k,
                     int64_t ldv, T* Y, int64_t ldy, int kid, T scale, int layout, void* ws, size_t ws_bytes,
-                    void* stream) {
+                    void* stream, const kmm::FuseArgs<T>* fuse = nullptr);
+
+template <typename T, typename E>
+int matmat_fused_t(const void* rows, int64_t n, const void* cols, int64_t m, int64_t d, const T* V, int64_t k,
+                   int64_t ldv, T* Y, int64_t ldy, int kid, T scale, int layout, const E* e, void* ws, size_t ws_bytes,
+                   void* stream) {
+    if (!e) return fail(RLAOPT_B200_EINVAL, "matmat_fused: null epilogue");
+    if ((e->addend && (e->ld_addend < k || e->addend_rows < 0)) || (e->rhs && (e->ld_rhs < k || e->rhs_rows < 0)))
+        return fail(RLAOPT_B200_EINVAL, "matmat_fused: bad addend / rhs stride");
+    if (!e->addend_idx && e->addend && e->addend_rows < n)
+        return fail(RLAOPT_B200_EINVAL, "matmat_fused: addend has %lld rows, product has %lld", (long long)e->addend_rows,
+                    (long long)n);
+    if (!e->rhs_idx && e->rhs && e->rhs_rows < n)
+        return fail(RLAOPT_B200_EINVAL, "matmat_fused: rhs has %lld rows, product has %lld", (long long)e->rhs_rows,
+                    (long long)n);
+    const bool want_gram = e->gram_lhs != nullptr && e->gram_cols > 0;
+    if (want_gram && (!e->gram_out || e->ld_gram_lhs < e->gram_cols))
+        return fail(RLAOPT_B200_EINVAL, "matmat_fused: Gram requested without output / with a bad stride");
+    if ((want_gram || e->sqnorm_out) && !kmm::fuse_reductions_supported<T>(k, want_gram ? e->gram_cols : 0))
+        return fail(RLAOPT_B200_EUNSUPPORTED, "matmat_fused: the fused reductions cover k <= 64 and gram_cols <= 64 (k=%lld)",
+                    (long long)k);
+    if (!Y && !want_gram && !e->sqnorm_out) return fail(RLAOPT_B200_EINVAL, "matmat_fused: nothing to compute");
+    kmm::FuseArgs<T> f;
+    f.alpha = e->alpha;
+    f.beta = e->beta;
+    f.addend = e->addend;
+    f.ld_addend = e->ld_addend;
+    f.addend_rows = e->addend_rows;
+    f.addend_idx = e->addend_idx;
+    f.gamma = e->gamma;
+    f.rhs = e->rhs;
+    f.ld_rhs = e->ld_rhs;
+    f.rhs_rows = e->rhs_rows;
+    f.rhs_idx = e->rhs_idx;
+    f.Y = Y;
+    f.ldy = ldy;
+    f.gram_lhs = want_gram ? e->gram_lhs : nullptr;
+    f.ld_gram_lhs = e->ld_gram_lhs;
+    f.gram_cols = want_gram ? (int)e->gram_cols : 0;
+    f.gram_out = e->gram_out;
+    f.want_sqnorm = e->sqnorm_out != nullptr;
+    f.sqnorm_out = e->sqnorm_out;
+    return matmat_packed_t<T>(rows, n, cols, m, d, V, k, ldv, Y, ldy, kid, scale, layout, ws, ws_bytes, stream, &f);
+}
+
+template <typename T>
+int matmat_packed_t(const void* rows, int64_t n, const void* cols, int64_t m, int64_t d, const T* V, int64_t k,
+                    int64_t ldv, T* Y, int64_t ldy, int kid, T scale, int layout, void* ws, size_t ws_bytes,
+                    void* stream, const kmm::FuseArgs<T>* fuse) {
     if (!valid_kernel(kid)) return fail(RLAOPT_B200_EINVAL, "matmat: unknown kernel id %d", kid);
-    if (n < 0 || m < 0 || d <= 0 || k < 0 || ldv < k || ldy < k)
+    if (n < 0 || m < 0 || d <= 0 || k < 0 || ldv < k || (Y && ldy < k))
         return fail(RLAOPT_B200_EINVAL, "matmat: bad shape n=%lld m=%lld d=%lld k=%lld ldv=%lld ldy=%lld", (long long)n,
                     (long long)m, (long long)d, (long long)k, (long long)ldv, (long long)ldy);
     if (n == 0 || k == 0) return 0;
-    if (!Y) return fail(RLAOPT_B200_EINVAL, "matmat: null output");
+    if (!Y && !fuse) return fail(RLAOPT_B200_EINVAL, "matmat: null output");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t red_bytes = fuse ? align256(kmm::fuse_workspace_bytes<T>(n, k, fuse->gram_cols, fuse->want_sqnorm)) : 0;
     if (m == 0) {  // empty sum
+        if (fuse) {  // the product is zero: only the addend / rhs terms remain (no partial sums: splits = 0)
+            if (red_bytes > 0 && (!ws || ws_bytes < red_bytes))
+                return fail(RLAOPT_B200_EWORKSPACE, "matmat_fused: workspace %zu < required %zu bytes", ws_bytes, red_bytes);
+            cudaError_t err = kmm::launch_fuse<T>(*fuse, nullptr, 0, n, k, T(0), ws, st);
+            return err == cudaSuccess ? 0 : cuda_fail(err, "matmat_fused(empty)");
+        }
         cudaError_t err = cudaMemset2DAsync(Y, ldy * sizeof(T), 0, k * sizeof(T), n, st);
         return err == cudaSuccess ? 0 : cuda_fail(err, "matmat(memset)");
     }
     if (!rows || !cols || !V) return fail(RLAOPT_B200_EINVAL, "matmat: null pointer");
     const int sms = sm_count();
     if (sms <= 0) return fail(RLAOPT_B200_EINVAL, "matmat: no CUDA device");
+    const bool keep = fuse != nullptr;
+    const size_t main_bytes = keep ? fused_main_bytes<T>(n, m, d, k, layout) : 0;
+    if (keep && (ws == nullptr || ws_bytes < main_bytes + red_bytes))
+        return fail(RLAOPT_B200_EWORKSPACE, "matmat_fused: workspace %zu < required %zu bytes", ws_bytes,
+                    main_bytes + red_bytes);
+    int splits = 1;
+    const T* part = static_cast<const T*>(ws);
     cudaError_t err;
     if (layout == RLAOPT_B200_LAYOUT_SIMT) {
         kmm::SimtArgs<T> a;
@@ -126,27 +204,34 @@ int matmat_packed_t(const void* rows, int64_t n, const void* cols, int64_t m, in
         a.scale = scale;
         a.kid = kid;
         a.stream = st;
-        const size_t need = kmm::simt_workspace_bytes<T>(n, m, k, sms);
+        const size_t need = kmm::simt_workspace_bytes<T>(n, m, k, sms, keep);
         if (need > 0 && (ws == nullptr || ws_bytes < need))
             return fail(RLAOPT_B200_EWORKSPACE, "matmat: workspace %zu < required %zu bytes", ws_bytes, need);
-        err = kmm::launch_simt<T>(a, sms, ws, ws_bytes);
+        err = kmm::launch_simt<T>(a, sms, ws, ws_bytes, keep, &splits);
     } else if (layout == RLAOPT_B200_LAYOUT_TC) {
         if constexpr (sizeof(T) == 4) {
             if (kid == kmm::KID_LAPLACE)
                 return fail(RLAOPT_B200_EUNSUPPORTED, "matmat: Laplace (L1) has no tensor-core path");
             if (!kmm::tc_supported_d(d))
                 return fail(RLAOPT_B200_EUNSUPPORTED, "matmat: d=%lld not supported by the tensor-core path", (long long)d);
-            const size_t need = kmm::tc_workspace_bytes(n, m, d, k, sms);
+            const size_t need = kmm::tc_workspace_bytes(n, m, d, k, sms, keep);
             if (need > 0 && (ws == nullptr || ws_bytes < need))
                 return fail(RLAOPT_B200_EWORKSPACE, "matmat: workspace %zu < required %zu bytes", ws_bytes, need);
-            err = kmm::launch_tc(rows, n, cols, m, d, V, k, ldv, Y, ldy, kid, scale, sms, ws, ws_bytes, st);
+            err = kmm::launch_tc(rows, n, cols, m, d, V, k, ldv, Y, ldy, kid, scale, sms, ws, ws_bytes, st, keep, &splits,
+                                 &part);
         } else {
             return fail(RLAOPT_B200_EUNSUPPORTED, "matmat: tensor-core path is fp32 only");
         }
     } else {
         return fail(RLAOPT_B200_EINVAL, "matmat: unknown layout %d", layout);
     }
-    return err == cudaSuccess ? 0 : cuda_fail(err, "matmat");
+    if (err != cudaSuccess) return cuda_fail(err, "matmat");
+    if (keep) {
+        err = kmm::launch_fuse<T>(*fuse, part, splits, n, k, fuse->alpha * scale,
+                                  static_cast<unsigned char*>(ws) + main_bytes, st);
+        if (err != cudaSuccess) return cuda_fail(err, "matmat_fused(output stage)");
+    }
+    return 0;
 }
 
 // one-shot entry, tensor-core layout: d floats for the center + the column-mean partial sums
@@ -286,6 +371,29 @@ int rlaopt_b200_matmat_packed_f64(const void* rows_packed, int64_t n, const void
                                   void* stream) {
     return matmat_packed_t<double>(rows_packed, n, cols_packed, m, d, V, k, ldv, Y, ldy, kernel_id, const_scaling,
                                    layout, workspace, workspace_bytes, stream);
+}
+
+size_t rlaopt_b200_matmat_fused_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int elem_bytes, int layout,
+                                                int64_t gram_cols, int want_sqnorm) {
+    return elem_bytes == 8 ? fused_workspace_t<double>(n, m, d, k, layout, gram_cols, want_sqnorm)
+                           : fused_workspace_t<float>(n, m, d, k, layout, gram_cols, want_sqnorm);
+}
+
+int rlaopt_b200_matmat_packed_fused_f32(const void* rows_packed, int64_t n, const void* cols_packed, int64_t m,
+                                        int64_t d, const float* V, int64_t k, int64_t ldv, float* Y, int64_t ldy,
+                                        int kernel_id, float const_scaling, int layout,
+                                        const rlaopt_b200_epilogue_f32* epilogue, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+    return matmat_fused_t<float>(rows_packed, n, cols_packed, m, d, V, k, ldv, Y, ldy, kernel_id, const_scaling, layout,
+                                 epilogue, workspace, workspace_bytes, stream);
+}
+int rlaopt_b200_matmat_packed_fused_f64(const void* rows_packed, int64_t n, const void* cols_packed, int64_t m,
+                                        int64_t d, const double* V, int64_t k, int64_t ldv, double* Y, int64_t ldy,
+                                        int kernel_id, double const_scaling, int layout,
+                                        const rlaopt_b200_epilogue_f64* epilogue, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+    return matmat_fused_t<double>(rows_packed, n, cols_packed, m, d, V, k, ldv, Y, ldy, kernel_id, const_scaling,
+                                  layout, epilogue, workspace, workspace_bytes, stream);
 }
 
 size_t rlaopt_b200_kernel_matmat_workspace_bytes(int64_t n_rows, int64_t m_cols, int64_t d, int64_t k, int elem_bytes,

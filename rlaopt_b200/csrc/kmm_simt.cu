@@ -408,24 +408,26 @@ void simt_plan(int64_t n, int64_t m, int64_t k, int sm_count, int* kc_out, int* 
 }
 
 template <typename T>
-size_t simt_workspace_bytes(int64_t n, int64_t m, int64_t k, int sm_count) {
+size_t simt_workspace_bytes(int64_t n, int64_t m, int64_t k, int sm_count, bool keep_partials) {
     int kc, splits, tps;
     simt_plan<T>(n, m, k, sm_count, &kc, &splits, &tps);
-    return splits > 1 ? (size_t)splits * (size_t)n * (size_t)k * sizeof(T) : 0;
+    return (splits > 1 || keep_partials) ? (size_t)splits * (size_t)n * (size_t)k * sizeof(T) : 0;
 }
 
 template <typename T>
-cudaError_t launch_simt(const SimtArgs<T>& a, int sm_count, void* workspace, size_t workspace_bytes) {
+cudaError_t launch_simt(const SimtArgs<T>& a, int sm_count, void* workspace, size_t workspace_bytes, bool keep_partials,
+                        int* splits_out) {
     int kc, splits, tps;
     simt_plan<T>(a.n, a.m, a.k, sm_count, &kc, &splits, &tps);
     const bool l1 = a.kid == KID_LAPLACE;
-    if (splits > 1) {
+    if (splits_out) *splits_out = splits;
+    if (splits > 1 || keep_partials) {
         const size_t need = (size_t)splits * (size_t)a.n * (size_t)a.k * sizeof(T);
         if (workspace == nullptr || workspace_bytes < need) return cudaErrorInvalidValue;
         T* part = static_cast<T*>(workspace);
         cudaError_t err = l1 ? launch_kc<T, true>(a, kc, splits, tps, part, a.k, a.n * a.k, T(1))
                              : launch_kc<T, false>(a, kc, splits, tps, part, a.k, a.n * a.k, T(1));
-        if (err != cudaSuccess) return err;
+        if (err != cudaSuccess || keep_partials) return err;
         const int64_t nk = a.n * a.k;
         const int threads = 256;
         kmm_split_reduce_kernel<T><<<(unsigned)((nk + threads - 1) / threads), threads, 0, a.stream>>>(
@@ -436,9 +438,9 @@ cudaError_t launch_simt(const SimtArgs<T>& a, int sm_count, void* workspace, siz
               : launch_kc<T, false>(a, kc, 1, tps, a.Y, a.ldy, 0, a.scale);
 }
 
-template cudaError_t launch_simt<float>(const SimtArgs<float>&, int, void*, size_t);
-template cudaError_t launch_simt<double>(const SimtArgs<double>&, int, void*, size_t);
-template size_t simt_workspace_bytes<float>(int64_t, int64_t, int64_t, int);
-template size_t simt_workspace_bytes<double>(int64_t, int64_t, int64_t, int);
+template cudaError_t launch_simt<float>(const SimtArgs<float>&, int, void*, size_t, bool, int*);
+template cudaError_t launch_simt<double>(const SimtArgs<double>&, int, void*, size_t, bool, int*);
+template size_t simt_workspace_bytes<float>(int64_t, int64_t, int64_t, int, bool);
+template size_t simt_workspace_bytes<double>(int64_t, int64_t, int64_t, int, bool);
 
 }  // namespace kmm

@@ -1682,10 +1682,11 @@ cudaError_t launch_tc_pack(const float* X, int64_t n, int64_t n_src, int64_t d, 
 // header fields the host reads back for its accuracy guard / index check (the copy is the caller's)
 size_t tc_stats_offset() { return offsetof(TcHeader, max_sqnorm_bits); }
 
-size_t tc_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count) {
+size_t tc_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, bool keep_partials) {
     TcPlan pl;
     if (!tc_plan(n, m, d, k, sm_count, &pl)) return 0;
-    return round_up((int64_t)pl.vimg_bytes, 256) + pl.part_bytes;
+    const size_t part = keep_partials ? (size_t)pl.splits * n * k * sizeof(float) : pl.part_bytes;
+    return round_up((int64_t)pl.vimg_bytes, 256) + part;
 }
 
 template <int KP, int NWG, bool M12, bool WIDE, int KV = 0, int KIDT = -1>
@@ -1759,11 +1760,13 @@ static cudaError_t launch_tc_kv(const TcParams& p, const TcPlan& pl, int64_t n, 
 
 cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packed, int64_t m, int64_t d,
                       const float* V, int64_t k, int64_t ldv, float* Y, int64_t ldy, int kid, float scale,
-                      int sm_count, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                      int sm_count, void* workspace, size_t workspace_bytes, cudaStream_t stream, bool keep_partials,
+                      int* splits_out, const float** part_out) {
     TcPlan pl;
     if (!tc_plan(n, m, d, k, sm_count, &pl)) return cudaErrorInvalidValue;
     const size_t v_bytes = (size_t)round_up((int64_t)pl.vimg_bytes, 256);
-    if (workspace == nullptr || workspace_bytes < v_bytes + pl.part_bytes) return cudaErrorInvalidValue;
+    const size_t part_bytes = keep_partials ? (size_t)pl.splits * n * k * sizeof(float) : pl.part_bytes;
+    if (workspace == nullptr || workspace_bytes < v_bytes + part_bytes) return cudaErrorInvalidValue;
     unsigned char* vimg = static_cast<unsigned char*>(workspace);
     float* part = reinterpret_cast<float*>(vimg + v_bytes);
     if (pl.kv) {
@@ -1799,7 +1802,9 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     p.kid = kid;
     p.sub_tiles = pl.sub_tiles;
     p.tiles_per_split = pl.tiles_per_split;
-    if (pl.splits > 1) {
+    if (splits_out) *splits_out = pl.splits;
+    if (part_out) *part_out = part;
+    if (pl.splits > 1 || keep_partials) {
         p.out = part;
         p.ldo = k;
         p.split_stride = n * k;
@@ -1821,7 +1826,7 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
         default: err = launch_tc_kp<128, 2>(p, pl, n, stream); break;
     }
     if (err != cudaSuccess) return err;
-    if (pl.splits > 1) return launch_split_reduce<float>(part, pl.splits, n, k, Y, ldy, scale, stream);
+    if (pl.splits > 1 && !keep_partials) return launch_split_reduce<float>(part, pl.splits, n, k, Y, ldy, scale, stream);
     return cudaSuccess;
 }
 

@@ -214,6 +214,17 @@ class _KernelLinOp(TwoSidedLinOp, ScaleMixin):
         P1, P2 = self._cache.get(self._layout_for(x))
         return ops.matmat_packed(P2, P1, x, self._kernel_id, self._scaling)
 
+    # -- fused products (rlaopt_b200.linops.apply_fused) -----------------------------
+    @staticmethod
+    def fused_reductions_ok(k: int, gram_cols: int = 0) -> bool:
+        return ops.fused_reductions_supported(k, gram_cols)
+
+    def matmat_fused(self, x: torch.Tensor, **epilogue):
+        """``alpha c K x + beta addend[..] + gamma rhs[..]`` with optional Gram / column norms, one pass
+        (``ops.matmat_packed_fused``): ``A P + reg P`` with ``P^T A P``, residuals with their norms."""
+        P1, P2 = self._cache.get(self._layout_for(x))
+        return ops.matmat_packed_fused(P1, P2, x, self._kernel_id, self._scaling, **epilogue)
+
     # -- oracles --------------------------------------------------------------
     def _oracle_packs(self, kind: str, blk: torch.Tensor, x: torch.Tensor):
         """Packs of ``A1[blk]`` (and ``A2[blk]``), memoised on the identity of ``blk``.
@@ -265,13 +276,21 @@ class _KernelLinOp(TwoSidedLinOp, ScaleMixin):
             Pr, Pc = self._oracle_packs(kind, blk, x)
             return ops.matmat_packed(Pr, Pc, x, self._kernel_id, self._scaling)
 
-        return LinOp(
+        def matmat_fused(x: torch.Tensor, **epilogue):
+            Pr, Pc = self._oracle_packs(kind, blk, x)
+            return ops.matmat_packed_fused(Pr, Pc, x, self._kernel_id, self._scaling, **epilogue)
+
+        op = LinOp(
             device=self.device,
             shape=torch.Size((blk.shape[0], n_cols)),
             matvec=matvec,
             matmat=matvec,
             dtype=self.dtype,
         )
+        # the block gradient of SAP / ASkotch in one pass: K[blk, :] Y + reg Y[blk] - B[blk] (sap.py:113-127)
+        op.matmat_fused = matmat_fused
+        op.fused_reductions_ok = ops.fused_reductions_supported
+        return op
 
     def row_oracle(self, blk: torch.Tensor) -> LinOp:
         """``c * K(A1[blk], A2)`` (``rlaopt/kernels/base.py:124-125``); forward products only."""

@@ -69,7 +69,32 @@ class ShardedKernelLinOp(RowShardedLinOp):
             dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
             return part
 
-        return LinOp(self.device, torch.Size((blk_dev.shape[0], self.shape[1])), matmat, matmat, dtype=self.dtype)
+        def matmat_fused(x, *, alpha=1.0, addend=None, beta=0.0, addend_idx=None, rhs=None, gamma=0.0, rhs_idx=None,
+                         gram_with=None, want_sqnorm=False, store=True):
+            """Block gradient of ASkotch (``sap.py:113-127``): the partial products are summed over the ranks, so the
+            ``beta`` / ``gamma`` terms are added by rank 0's output stage only and ride the same all-reduce."""
+            if gram_with is not None or want_sqnorm or not store:
+                raise NotImplementedError("the distributed row oracle fuses the element-wise terms only")
+            first = self.rank == 0
+            if local is None:
+                part = x.new_zeros((blk_dev.shape[0],) + tuple(x.shape[1:]))
+                if first:
+                    for t, idx, coef in ((addend, addend_idx, beta), (rhs, rhs_idx, gamma)):
+                        if t is not None:
+                            rows_t = t if idx is None else t[idx.to(self.device)]
+                            part.add_(rows_t.reshape(part.shape), alpha=coef)
+            else:
+                part, _, _ = local.matmat_fused(
+                    x[clo:chi], alpha=alpha, addend=addend if first else None, beta=beta, addend_idx=addend_idx,
+                    rhs=rhs if first else None, gamma=gamma, rhs_idx=rhs_idx)
+                part = part.contiguous()
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+            return part, None, None
+
+        op = LinOp(self.device, torch.Size((blk_dev.shape[0], self.shape[1])), matmat, matmat, dtype=self.dtype)
+        op.matmat_fused = matmat_fused
+        op.fused_reductions_ok = lambda k, g=0: False
+        return op
 
     def blk_oracle(self, blk: torch.Tensor) -> LinOp:
         blk_dev = blk.to(self.device)

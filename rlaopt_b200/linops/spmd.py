@@ -95,6 +95,59 @@ class RowShardedLinOp(_BaseLinOp):
     def _matvec(self, x: torch.Tensor) -> torch.Tensor:
         return self._gather_rows(self.local_matmat(x))
 
+    # -- fused products (rlaopt_b200.linops.apply_fused) ---------------------
+    def fused_reductions_ok(self, k: int, gram_cols: int = 0) -> bool:
+        ok = getattr(self.local_op, "fused_reductions_ok", None)
+        return bool(ok and ok(k, gram_cols)) if self.local_op is not None else (1 <= k <= 64 and gram_cols <= 64)
+
+    def matmat_fused(self, x: torch.Tensor, *, alpha=1.0, addend=None, beta=0.0, addend_idx=None, rhs=None, gamma=0.0,
+                     rhs_idx=None, gram_with=None, want_sqnorm=False, store=True):
+        """Every rank runs the fused output stage on its own row block (its rows of ``addend`` / ``rhs`` /
+        ``gram_with``); the row blocks are all-gathered and the k x k Gram partials and the column norms are
+        all-reduced together in one small buffer -- the only reductions block PCG needs across ranks
+        (``rlaopt/solvers/pcg.py:58-61``)."""
+        lo, hi = self.lo, self.hi
+        k = 1 if x.ndim == 1 else x.shape[1]
+        g = 0 if gram_with is None else (1 if gram_with.ndim == 1 else gram_with.shape[1])
+
+        def rows_of(t, idx):
+            if t is None:
+                return None, None
+            if idx is None:
+                return t[lo:hi], None
+            return t, idx.to(t.device)[lo:hi]
+
+        Y_loc = gram = sqn = None
+        if self.local_op is not None and hasattr(self.local_op, "matmat_fused"):
+            a_t, a_i = rows_of(addend, addend_idx)
+            r_t, r_i = rows_of(rhs, rhs_idx)
+            Y_loc, gram, sqn = self.local_op.matmat_fused(
+                x, alpha=alpha, addend=a_t, beta=beta, addend_idx=a_i, rhs=r_t, gamma=gamma, rhs_idx=r_i,
+                gram_with=None if gram_with is None else gram_with[lo:hi], want_sqnorm=want_sqnorm, store=store)
+        elif self.local_op is not None:  # a local operator without a fused stage: separate passes on the block
+            from .fused import apply_fused
+
+            a_t, a_i = rows_of(addend, addend_idx)
+            r_t, r_i = rows_of(rhs, rhs_idx)
+            Y_loc, gram, sqn = apply_fused(
+                self.local_op, x, alpha=alpha, addend=a_t, beta=beta, addend_idx=a_i, rhs=r_t, gamma=gamma, rhs_idx=r_i,
+                gram_with=None if gram_with is None else gram_with[lo:hi], want_sqnorm=want_sqnorm, store=store)
+        if g or want_sqnorm:
+            red = x.new_zeros((g + (1 if want_sqnorm else 0)) * k)
+            if gram is not None:
+                red[: g * k] = gram.reshape(-1)
+            if sqn is not None:
+                red[g * k:] = sqn
+            dist.all_reduce(red, op=dist.ReduceOp.SUM, group=self.group)
+            gram = red[: g * k].reshape(g, k) if g else None
+            sqn = red[g * k:] if want_sqnorm else None
+        Y = None
+        if store:
+            if Y_loc is None:
+                Y_loc = x.new_zeros((0,) if x.ndim == 1 else (0, k))
+            Y = self._gather_rows(Y_loc)
+        return Y, gram, sqn
+
     def _matmat(self, x: torch.Tensor) -> torch.Tensor:
         return self._matvec(x)
 

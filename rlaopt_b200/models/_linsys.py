@@ -14,6 +14,7 @@ from warnings import warn
 
 import torch
 
+from rlaopt_b200.linops.fused import apply_fused
 from rlaopt_b200.linops.types import _is_linop_or_torch_tensor
 from rlaopt_b200.utils import Logger, _is_callable, _is_nonneg_float, _is_torch_tensor
 
@@ -55,6 +56,7 @@ class Model:
         return kwargs
 
     def _train(self, logger: Logger, termination_fn: Callable, solver, max_iters: int):
+        self._solver = solver  # the metrics may read the solver's own residual (LinSys, residual="recurrence")
         log = {0: logger._compute_log(0, solver.W)}
         if termination_fn(log[0]["metrics"]["internal_metrics"]):
             return solver.W, log
@@ -80,6 +82,8 @@ class LinSys(Model):
         self._A_blk_oracle = A_blk_oracle
         self._mask = torch.ones(self._B.shape[1], dtype=torch.bool)
         self._B_norm = None
+        self._residual_mode = "true"
+        self._metrics_from_recurrence = False
 
     A = property(lambda self: self._A)
     B = property(lambda self: self._B)
@@ -105,19 +109,58 @@ class LinSys(Model):
             self._B_norm = torch.linalg.norm(self._B, dim=0, ord=2)
         return self._B_norm
 
+    def _true_sq_residual(self, W: torch.Tensor) -> torch.Tensor:
+        """Squared column norms of ``B - (A W + reg W)``: one fused pass, the residual itself is never stored."""
+        _, _, sqn = apply_fused(self.A, W, alpha=-1.0, addend=W, beta=-self.reg, rhs=self.B, gamma=1.0,
+                                want_sqnorm=True, store=False)
+        return sqn
+
     def _compute_internal_metrics(self, W: torch.Tensor):
-        AW = self.A @ W
-        abs_res = torch.linalg.norm(self.B - (AW + self.reg * W), dim=0, ord=2)
+        """``{"abs_res", "rel_res"}`` per right-hand side (``linsys.py:96-99``).
+
+        ``residual="true"`` (default, the reference's behaviour): one full product per logged iteration, with the
+        subtraction and the column norms folded into the product's output stage.  ``residual="recurrence"`` (opt-in,
+        block PCG only): the norms of the residual the solver already carries, ``R_t = R_{t-1} - (A P + reg P) alpha``
+        (``pcg.py:64-67``) -- a logged iteration then costs one product instead of two.  The recurrence drifts from
+        the true residual by rounding, so convergence is *confirmed* once with the true residual before the solve
+        stops; if the confirmation fails the solve continues on true residuals."""
+        solver = getattr(self, "_solver", None)
+        R = getattr(solver, "R", None)
+        self._metrics_from_recurrence = False
+        if self._residual_mode == "recurrence" and R is not None and solver.W is W:
+            abs_res = torch.linalg.norm(R, dim=0, ord=2)
+            self._metrics_from_recurrence = True
+        else:
+            abs_res = self._true_sq_residual(W).sqrt()
         return {"abs_res": abs_res, "rel_res": abs_res / self._rhs_norms()}
 
     def _check_termination_criteria(self, internal_metrics: dict, atol: float, rtol: float):
         tol = torch.clamp(rtol * self._rhs_norms(), min=atol)
         self._mask = (internal_metrics["abs_res"] > tol).cpu()
-        return not bool(self._mask.any())
+        done = not bool(self._mask.any())
+        if done and self._metrics_from_recurrence:
+            # confirm with the true residual (one product, once per solve when the recurrence is accurate)
+            abs_res = self._true_sq_residual(self._solver.W).sqrt()
+            internal_metrics["abs_res"], internal_metrics["rel_res"] = abs_res, abs_res / self._rhs_norms()
+            self._mask = (abs_res > tol).cpu()
+            done = not bool(self._mask.any())
+            if not done:
+                self._residual_mode = "true"
+        return done
 
     def solve(self, solver_config, W_init, callback_fn=None, callback_args=[], callback_kwargs={},
-              callback_freq=10, log_in_wandb=False, wandb_init_kwargs=None):
+              callback_freq=10, log_in_wandb=False, wandb_init_kwargs=None, *, residual: str | None = None):
+        """``residual`` (extension, keyword only): ``"true"`` -- the reference's metric, one extra product per logged
+        iteration -- or ``"recurrence"``, see :meth:`_compute_internal_metrics`; default from
+        ``RLAOPT_B200_RESIDUAL`` (``"true"``)."""
+        import os
+
         from rlaopt_b200.solvers import _get_solver, _get_solver_name, _is_solver_config
+
+        mode = residual if residual is not None else os.environ.get("RLAOPT_B200_RESIDUAL", "true")
+        if mode not in ("true", "recurrence"):
+            raise ValueError(f"residual must be 'true' or 'recurrence', got {mode!r}")
+        self._residual_mode = mode
 
         _is_solver_config(solver_config, "solver_config")
         _is_torch_tensor(W_init, "W_init")

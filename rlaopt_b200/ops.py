@@ -292,6 +292,116 @@ def matmat_packed(
     return Y[:, 0] if vec else Y
 
 
+def _rows_operand(t: torch.Tensor, k: int, name: str, like: torch.Tensor) -> torch.Tensor:
+    """(rows, k) operand of the fused output stage: 2-D view, unit column stride, on the product's device."""
+    if t.device != like.device or t.dtype != like.dtype:
+        raise ValueError(f"{name} must live on {like.device} with dtype {like.dtype}")
+    t2 = t.unsqueeze(1) if t.ndim == 1 else t
+    if t2.ndim != 2 or t2.shape[1] != k:
+        raise ValueError(f"{name} must have {k} column(s), got shape {tuple(t.shape)}")
+    if (t2.shape[1] > 1 and t2.stride(1) != 1) or (t2.shape[0] > 1 and t2.stride(0) < t2.shape[1]):
+        t2 = t2.contiguous()
+    return t2
+
+
+def matmat_packed_fused(
+    rows: PackedPoints,
+    cols: PackedPoints,
+    V: torch.Tensor,
+    kernel: Union[str, int],
+    const_scaling: float = 1.0,
+    *,
+    alpha: float = 1.0,
+    addend: Optional[torch.Tensor] = None,
+    beta: float = 0.0,
+    addend_idx: Optional[torch.Tensor] = None,
+    rhs: Optional[torch.Tensor] = None,
+    gamma: float = 0.0,
+    rhs_idx: Optional[torch.Tensor] = None,
+    gram_with: Optional[torch.Tensor] = None,
+    want_sqnorm: bool = False,
+    store: bool = True,
+):
+    """``Y = alpha * c * K(rows, cols) @ V + beta * addend[addend_idx] + gamma * rhs[rhs_idx]`` with the Gram
+    matrix ``gram_with^T Y`` and the squared column norms of ``Y`` taken in the same pass (C entry
+    ``rlaopt_b200_matmat_packed_fused_*``).  Returns ``(Y or None, gram or None, sqnorm or None)``; ``store=False``
+    skips writing ``Y`` (only the reductions are wanted -- no n x k result exists anywhere)."""
+    global LAUNCH_COUNT
+    kid = kernel_id(kernel)
+    _require_cuda(V, "V")
+    if rows.layout != cols.layout or rows.dtype != cols.dtype or rows.d != cols.d:
+        raise ValueError("packed operands disagree in layout / dtype / feature count")
+    if not _same_center(rows.center, cols.center):
+        raise ValueError("packed operands were shifted by different centers: K(x - c1, y - c2) is not K(x, y)")
+    if V.device != rows.device or cols.device != rows.device:
+        raise ValueError("operands and V must be on the same device")
+    if V.dtype != rows.dtype:
+        raise ValueError(f"V has dtype {V.dtype}, operator has dtype {rows.dtype}")
+    if V.ndim not in (1, 2):
+        raise ValueError(f"x must be a 1D or 2D tensor. Received {V.ndim}D tensor.")
+    if V.shape[0] != cols.n:
+        raise ValueError(f"dimension mismatch: operator has {cols.n} columns, V has {V.shape[0]} rows")
+    vec = V.ndim == 1
+    k = 1 if vec else V.shape[1]
+    Vm = _rows_operand(V, k, "V", V)
+    n = rows.n
+    lib = _lib.load()
+    f32 = V.dtype == torch.float32
+    epi = (_lib.EpilogueF32 if f32 else _lib.EpilogueF64)()
+    keep = []  # tensors the launch reads: kept alive until it is enqueued
+    epi.alpha, epi.beta, epi.gamma = float(alpha), float(beta), float(gamma)
+    for name, t, idx in (("addend", addend, addend_idx), ("rhs", rhs, rhs_idx)):
+        if t is None:
+            continue
+        t2 = _rows_operand(t, k, name, V)
+        if idx is not None:
+            idx = _check_index(idx, t2.shape[0], V.device)
+            if idx.shape[0] != n:
+                raise ValueError(f"{name}_idx must have one entry per output row ({n}), got {idx.shape[0]}")
+        elif t2.shape[0] != n:
+            raise ValueError(f"{name} must have {n} rows, got {t2.shape[0]}")
+        keep += [t2, idx]
+        setattr(epi, name, t2.data_ptr())
+        setattr(epi, f"ld_{name}", t2.stride(0) if t2.shape[0] > 1 else k)
+        setattr(epi, f"{name}_rows", t2.shape[0])
+        setattr(epi, f"{name}_idx", _ptr(idx))
+    gram = sqn = None
+    gcols = 0
+    with torch.cuda.device(V.device):
+        if gram_with is not None:
+            gcols = 1 if gram_with.ndim == 1 else gram_with.shape[1]
+            L = _rows_operand(gram_with, gcols, "gram_with", V)
+            if L.shape[0] != n:
+                raise ValueError(f"gram_with must have {n} rows, got {L.shape[0]}")
+            gram = torch.empty((gcols, k), dtype=V.dtype, device=V.device)
+            keep.append(L)
+            epi.gram_lhs, epi.ld_gram_lhs, epi.gram_cols = L.data_ptr(), (L.stride(0) if n > 1 else gcols), gcols
+            epi.gram_out = gram.data_ptr()
+        if want_sqnorm:
+            sqn = torch.empty(k, dtype=V.dtype, device=V.device)
+            epi.sqnorm_out = sqn.data_ptr()
+        Y = torch.empty((n, k), dtype=V.dtype, device=V.device) if store else None
+        elem = V.element_size()
+        ws_bytes = lib.rlaopt_b200_matmat_fused_workspace_bytes(n, cols.n, rows.d, k, elem, rows.layout, gcols,
+                                                                int(want_sqnorm))
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=V.device)
+        fn = getattr(lib, f"rlaopt_b200_matmat_packed_fused_{_SUFFIX[V.dtype]}")
+        ldv = Vm.stride(0) if Vm.shape[0] > 1 else k
+        rc = fn(_ptr(rows.buf), n, _ptr(cols.buf), cols.n, rows.d, _ptr(Vm), k, ldv, _ptr(Y), k, kid,
+                float(const_scaling), rows.layout, ctypes.addressof(epi), _ptr(ws), ws_bytes, _stream(V.device))
+        _lib.check(rc, "matmat_packed_fused")
+    LAUNCH_COUNT += 3 + (1 if (gram is not None or want_sqnorm) else 0)  # V pack, fused kernel, output stage (+ reduce)
+    del keep
+    if Y is not None and vec:
+        Y = Y[:, 0]
+    return Y, gram, sqn
+
+
+def fused_reductions_supported(k: int, gram_cols: int = 0) -> bool:
+    """The Gram / column-norm reductions of the fused output stage cover k <= 64 and gram_cols <= 64."""
+    return 1 <= k <= 64 and 0 <= gram_cols <= 64
+
+
 def kernel_matmat(
     A1: torch.Tensor,
     A2: torch.Tensor,

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import torch
 
+from rlaopt_b200.linops.fused import apply_fused
 from rlaopt_b200.preconditioners import PreconditionerConfig, _get_precond
 
 from ._solver import Solver
@@ -30,8 +31,8 @@ class PCG(Solver):
         self.device = device
         self._W = W_init.clone()
         self.P = self._get_precond()
-        # R = B - (A + reg I) W,  Z = P^{-1} R,  first directions = Z,  RZ = R^T Z
-        self.R = system.B - self._apply(self._W)
+        # R = B - (A + reg I) W in the operator's output stage,  Z = P^{-1} R,  first directions = Z,  RZ = R^T Z
+        self.R, _, _ = apply_fused(system.A, self._W, alpha=-1.0, addend=self._W, beta=-system.reg, rhs=system.B, gamma=1.0)
         self.Z = self.P._inv @ self.R
         self.P_ = self.Z.clone()
         self.RZ = self.R.T @ self.Z
@@ -40,10 +41,10 @@ class PCG(Solver):
     def W(self):
         return self._W
 
-    def _apply(self, X: torch.Tensor) -> torch.Tensor:
-        """(A + reg I) X"""
-        Y = self.system.A @ X
-        return Y.add_(X, alpha=self.system.reg) if Y.data_ptr() != X.data_ptr() else Y + self.system.reg * X
+    def _apply(self, X: torch.Tensor, gram: bool = False):
+        """``(A + reg I) X`` and, on request, ``X^T (A + reg I) X`` from the same pass (``pcg.py:58-61``)."""
+        Y, G, _ = apply_fused(self.system.A, X, addend=X, beta=self.system.reg, gram_with=X if gram else None)
+        return (Y, G) if gram else Y
 
     def _get_precond(self):
         P = _get_precond(self.precond_config)
@@ -62,8 +63,8 @@ class PCG(Solver):
 
     def _step_all(self):
         D = self.P_
-        AD = self._apply(D)
-        alpha = _small_solve(D.T @ AD, self.RZ)
+        AD, G = self._apply(D, gram=True)
+        alpha = _small_solve(G, self.RZ)
         self._W.addmm_(D, alpha)
         self.R.addmm_(AD, alpha, alpha=-1.0)
         self.Z = self.P._inv @ self.R
@@ -76,8 +77,8 @@ class PCG(Solver):
         idx = torch.nonzero(mask).squeeze(-1)
         D = self.P_[:, idx]
         RZ = self.RZ[idx][:, idx]
-        AD = self._apply(D)
-        alpha = _small_solve(D.T @ AD, RZ)
+        AD, G = self._apply(D.contiguous(), gram=True)
+        alpha = _small_solve(G, RZ)
         self._W[:, idx] += D @ alpha
         R_act = self.R[:, idx] - AD @ alpha
         self.R[:, idx] = R_act

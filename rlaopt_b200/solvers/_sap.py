@@ -27,6 +27,7 @@ import numpy as np
 import torch
 
 from rlaopt_b200.linops import LinOp
+from rlaopt_b200.linops.fused import apply_fused
 from rlaopt_b200.preconditioners import (IdentityConfig, NewtonConfig, NystromConfig, Preconditioner,
                                          PreconditionerConfig, _get_precond)
 from rlaopt_b200.spectral_estimators import randomized_powering
@@ -126,8 +127,9 @@ class SAP(Solver):
         return max_eig ** (-1.0)
 
     def _get_block_update(self, W: torch.Tensor, B: torch.Tensor, blk: torch.Tensor, blk_precond: Preconditioner):
-        grad = self.system.A_row_oracle(blk) @ W
-        grad.add_(W[blk], alpha=self.system.reg).sub_(B[blk])
+        # A[blk, :] W + reg W[blk] - B[blk] in the row oracle's output stage (sap.py:113-127)
+        grad, _, _ = apply_fused(self.system.A_row_oracle(blk), W, addend=W, beta=self.system.reg, addend_idx=blk,
+                                 rhs=B, gamma=-1.0, rhs_idx=blk)
         return blk_precond._inv @ grad
 
     def _step(self):

@@ -148,3 +148,49 @@ def test_preconditioner_algebra():
         assert torch.linalg.norm(approx - (G @ G.T).to(dtype)) <= (1e-8 if dtype == torch.float64 else 5e-3) * torch.linalg.norm(G @ G.T)
     with pytest.raises(NotImplementedError):
         _get_precond(SkPreConfig(sketch_size=10, rho=0.1))
+
+
+def test_apply_fused_generic_path_and_recurrence_residual_on_cpu():
+    """``apply_fused`` over a dense operator (separate passes) and the opt-in recurrence residual of ``LinSys.solve``
+    with the solver stack on the CPU: same iteration count and solution as the true-residual run."""
+    import torch
+
+    from rlaopt_b200.linops import SymmetricLinOp, apply_fused
+    from rlaopt_b200.models import LinSys
+    from rlaopt_b200.preconditioners import NystromConfig
+    from rlaopt_b200.solvers import PCGConfig
+
+    torch.manual_seed(0)
+    n, k = 400, 3
+    Z = torch.randn(n, 40, dtype=torch.float64)
+    K = Z @ Z.T / 40
+    cpu = torch.device("cpu")
+    counts = {"mm": 0}
+
+    def mm(V):
+        counts["mm"] += 1
+        return K @ V
+
+    A = SymmetricLinOp(cpu, torch.Size((n, n)), mm, mm, dtype=torch.float64)
+    W, B, L = torch.randn(n, k, dtype=torch.float64), torch.randn(n, k, dtype=torch.float64), torch.randn(n, 2, dtype=torch.float64)
+    idx = torch.randperm(n)
+    Y, G, S = apply_fused(A, W, alpha=-1.0, addend=W, beta=-0.3, addend_idx=idx, rhs=B, gamma=1.0, gram_with=L,
+                          want_sqnorm=True)
+    ref = B - (K @ W + 0.3 * W[idx])
+    assert torch.allclose(Y, ref) and torch.allclose(G, L.T @ ref) and torch.allclose(S, (ref * ref).sum(0))
+    out = {}
+    for mode in ("true", "recurrence"):
+        counts["mm"] = 0
+        system = LinSys(A, B, reg=0.3)
+        cfg = PCGConfig(device=cpu, max_iters=100, rtol=1e-9, precond_config=NystromConfig(rank=30, rho=0.3, sketch="gauss"))
+        torch.manual_seed(1)
+        Ws, log = system.solve(cfg, torch.zeros(n, k, dtype=torch.float64), callback_freq=1, residual=mode)
+        out[mode] = (Ws, max(log), counts["mm"])
+    assert out["true"][1] == out["recurrence"][1]
+    assert torch.allclose(out["true"][0], out["recurrence"][0], rtol=1e-8, atol=1e-10)
+    it = out["true"][1]
+    assert out["true"][2] == 1 + 1 + 1 + 2 * it and out["recurrence"][2] == 1 + 1 + it + 1
+    import pytest
+
+    with pytest.raises(ValueError):
+        LinSys(A, B, reg=0.3).solve(cfg, torch.zeros(n, k, dtype=torch.float64), residual="bogus")
