@@ -84,6 +84,7 @@ class LinSys(Model):
         self._B_norm = None
         self._residual_mode = "true"
         self._metrics_from_recurrence = False
+        self._failed_confirmations = 0
 
     A = property(lambda self: self._A)
     B = property(lambda self: self._B)
@@ -140,12 +141,22 @@ class LinSys(Model):
         done = not bool(self._mask.any())
         if done and self._metrics_from_recurrence:
             # confirm with the true residual (one product, once per solve when the recurrence is accurate)
-            abs_res = self._true_sq_residual(self._solver.W).sqrt()
+            R_true, _, sqn = apply_fused(self.A, self._solver.W, alpha=-1.0, addend=self._solver.W, beta=-self.reg,
+                                         rhs=self.B, gamma=1.0, want_sqnorm=True)
+            abs_res = sqn.sqrt() if sqn is not None else torch.linalg.norm(R_true, dim=0, ord=2)
             internal_metrics["abs_res"], internal_metrics["rel_res"] = abs_res, abs_res / self._rhs_norms()
             self._mask = (abs_res > tol).cpu()
             done = not bool(self._mask.any())
             if not done:
-                self._residual_mode = "true"
+                # the recurrence had drifted: restart the solver from the true residual (columns that were frozen
+                # carry no search direction any more) and keep going; after three failed confirmations every
+                # logged iteration evaluates the true residual again
+                self._failed_confirmations += 1
+                restart = getattr(self._solver, "_restart_from_residual", None)
+                if restart is not None:
+                    restart(R_true)
+                if restart is None or self._failed_confirmations >= 3:
+                    self._residual_mode = "true"
         return done
 
     def solve(self, solver_config, W_init, callback_fn=None, callback_args=[], callback_kwargs={},
@@ -161,6 +172,7 @@ class LinSys(Model):
         if mode not in ("true", "recurrence"):
             raise ValueError(f"residual must be 'true' or 'recurrence', got {mode!r}")
         self._residual_mode = mode
+        self._failed_confirmations = 0
 
         _is_solver_config(solver_config, "solver_config")
         _is_torch_tensor(W_init, "W_init")

@@ -46,6 +46,14 @@ class PCG(Solver):
         Y, G, _ = apply_fused(self.system.A, X, addend=X, beta=self.system.reg, gram_with=X if gram else None)
         return (Y, G) if gram else Y
 
+    def _restart_from_residual(self, R: torch.Tensor) -> None:
+        """Restart block CG at the current iterate from a freshly evaluated residual (``LinSys`` calls this when the
+        true residual contradicts the recurrence): new preconditioned residual, steepest-descent directions, Gram."""
+        self.R = R.clone() if R.data_ptr() == self.R.data_ptr() else R
+        self.Z = self.P._inv @ self.R
+        self.P_ = self.Z.clone()
+        self.RZ = self.R.T @ self.Z
+
     def _get_precond(self):
         P = _get_precond(self.precond_config)
         P._update(self.system.A, self.device)

@@ -11,7 +11,7 @@ dev = torch.device("cuda:0")
 mode = sys.argv[1]
 if mode == "askotch":
     n, max_iters = int(sys.argv[2]), int(sys.argv[3])
-    d, k, reg = 16, 1, 1e-2
+    d, k, reg = 16, 1, float(sys.argv[4]) if len(sys.argv) > 4 else 1e-2
     os.environ["RLAOPT_B200_SAP_SAMPLER"] = "device"
     g = torch.Generator(device=dev).manual_seed(0)
     X = torch.randn(n, d, generator=g, device=dev) / d**0.5
@@ -19,7 +19,7 @@ if mode == "askotch":
     A = RBFLinOp(X, X, KernelConfig(lengthscale=1.0))
     system = LinSys(A, B, reg=reg, A_row_oracle=A.row_oracle, A_blk_oracle=A.blk_oracle)
     cfg = SAPConfig(precond_config=NystromConfig(rank=100, rho=reg), max_iters=max_iters, atol=1e-30, rtol=1e-4,
-                    blk_sz=n // 100, accel_config=SAPAccelConfig(mu=reg, nu=100.0), device=dev)
+                    blk_sz=n // 100, accel_config=SAPAccelConfig(mu=reg, nu=float(sys.argv[5]) if len(sys.argv) > 5 else 100.0), device=dev)
     torch.manual_seed(0)
     t0 = time.perf_counter()
     W, log = system.solve(cfg, torch.zeros(n, k, device=dev), callback_freq=100)
@@ -35,13 +35,18 @@ else:
     B = torch.randn(n, k, generator=g, device=dev)
     A = RBFLinOp(X, X, KernelConfig(lengthscale=1.0))
     system = LinSys(A, B, reg=reg)
-    cfg = PCGConfig(device=dev, max_iters=200, rtol=1e-4, atol=1e-30,
-                    precond_config=NystromConfig(rank=rank, rho=reg, sketch="gauss"))
+    cfg = PCGConfig(device=dev, max_iters=int(sys.argv[4]) if len(sys.argv) > 4 else 60, rtol=float(sys.argv[5]) if len(sys.argv) > 5 else 1e-3,
+                    atol=1e-30, precond_config=NystromConfig(rank=rank, rho=reg, sketch="gauss"))
     torch.manual_seed(0)
     t0 = time.perf_counter()
-    W, log = system.solve(cfg, torch.zeros(n, k, device=dev), callback_freq=5)
+    try:
+        W, log = system.solve(cfg, torch.zeros(n, k, device=dev), callback_freq=1, residual="recurrence")
+    except Exception as e:
+        print("ERR", type(e).__name__, str(e)[:200]); sys.exit(0)
     torch.cuda.synchronize()
     print(f"pcg n={n} reg={reg}: {time.perf_counter() - t0:.1f} s wall, {max(log)} iterations")
     for it in sorted(log):
         r = log[it]['metrics']['internal_metrics']['rel_res']
         print(f"  iter {it:4d} cum {log[it]['cum_time']:7.2f} s rel_res max {float(r.max()):.3e} min {float(r.min()):.3e}")
+    true = system._true_sq_residual(W).sqrt() / system._rhs_norms()
+    print(f"  true rel_res max {float(true.max()):.3e}")

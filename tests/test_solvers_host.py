@@ -194,3 +194,39 @@ def test_apply_fused_generic_path_and_recurrence_residual_on_cpu():
 
     with pytest.raises(ValueError):
         LinSys(A, B, reg=0.3).solve(cfg, torch.zeros(n, k, dtype=torch.float64), residual="bogus")
+
+
+def test_recurrence_residual_failed_confirmation_restarts_cleanly():
+    """A tolerance below the fp32 floor: the recurrence residual keeps shrinking, the confirming true residual does
+    not.  The solver is restarted from the true residual (frozen columns get directions again -- no division by a
+    zeroed Gram entry), after three failed confirmations the metric is the true residual; nothing becomes non-finite
+    and the reported residuals are true residuals."""
+    import torch
+
+    from rlaopt_b200.linops import SymmetricLinOp
+    from rlaopt_b200.models import LinSys
+    from rlaopt_b200.preconditioners import NystromConfig
+    from rlaopt_b200.solvers import PCGConfig
+
+    g = torch.Generator().manual_seed(0)
+    n, d, k = 1500, 64, 6
+    X = torch.randn(n, d, generator=g, dtype=torch.float64) / d**0.5
+    sq = (X * X).sum(1)
+    K = torch.exp(-0.5 * (sq[:, None] + sq[None, :] - 2 * X @ X.T).clamp_min(0)).float()
+    B = torch.randn(n, k, generator=g)
+    B[:, :3] = K @ B[:, :3]  # smooth right-hand sides converge earlier: the mask becomes partial
+    cpu = torch.device("cpu")
+    A = SymmetricLinOp(cpu, torch.Size((n, n)), lambda v: K @ v, lambda V: K @ V, dtype=torch.float32)
+    system = LinSys(A, B, reg=0.2)
+    cfg = PCGConfig(device=cpu, max_iters=60, rtol=2e-7, atol=1e-30,
+                    precond_config=NystromConfig(rank=100, rho=0.2, sketch="gauss"))
+    torch.manual_seed(0)
+    W, log = system.solve(cfg, torch.zeros(n, k), callback_freq=1, residual="recurrence")
+    assert torch.isfinite(W).all()
+    last = log[max(log)]["metrics"]["internal_metrics"]["rel_res"]
+    assert torch.isfinite(last).all()
+    true = torch.linalg.norm(B - (K @ W + 0.2 * W), dim=0) / torch.linalg.norm(B, dim=0)
+    assert float(true.max()) < 1e-4  # converged to the fp32 floor
+    assert system._failed_confirmations >= 1
+    if system._residual_mode == "true":  # the last logged metric is then a true residual
+        assert torch.allclose(last, true, rtol=1e-3, atol=1e-7)
