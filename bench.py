@@ -623,16 +623,28 @@ def run_ours(args) -> int:
     checksum = float(Y.double().abs().sum().item())
 
     # ---- end to end through the public API with host buffers ----------------------------------
-    # the caller of the reference's distributed operator is one process: rank 0 reads the result back
-    Yh = torch.empty((n, k), dtype=torch.float32).pin_memory() if rank == 0 else None
+    # N = 1: the result is read back into pinned host memory.  N > 1: the caller's result buffer is host memory that
+    # every rank maps and pins (SharedPinnedTensor); each rank delivers its own row block over its own PCIe link
+    # (RowShardedLinOp.matmat_to_host) -- the reference hands the result of its distributed operator to one process
+    # through host memory too (rlaopt/linops/base.py:259-276), there via pickled per-worker CPU tensors
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    shared_out = None
+    if world > 1:
+        from rlaopt_b200.utils import SharedPinnedTensor
+
+        shared_out = SharedPinnedTensor("bench_Y", (n, k), torch.float32)
+        Yh = shared_out.tensor
+    else:
+        Yh = torch.empty((n, k), dtype=torch.float32).pin_memory()
 
     def e2e_step():
         op_e = build(Xp)  # H2D of X, operator construction (packing happens on first product)
-        Yd = op_e @ replicate_from_host(Vp, dev)  # H2D of V, fused matmat (+ all-gather)
-        if Yh is not None:
-            Yh.copy_(Yd, non_blocking=True)  # D2H of the result
-        torch.cuda.synchronize(dev)
+        Vd = replicate_from_host(Vp, dev)  # H2D of V
+        if world > 1:
+            op_e.matmat_to_host(Vd, Yh)  # fused matmat on the rank's rows, D2H of the row block, barrier
+        else:
+            Yh.copy_(op_e @ Vd, non_blocking=True)  # fused matmat, D2H of the result
+            torch.cuda.synchronize(dev)
 
     for _ in range(2):  # warm: allocator growth and the first NCCL calls on these message sizes stay outside the timing
         e2e_step()
@@ -645,6 +657,10 @@ def run_ours(args) -> int:
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n * n / e2e_s.item() / 1e9
+    e2e_checksum = float(Yh.double().abs().sum().item()) if rank == 0 else None  # the host result is complete on rank 0
+    if shared_out is not None:
+        shared_out.close()
+    del Yh
 
     # ---- solve-level BASELINE configs (8 GPUs; --solve-legs forces them at another N) ----------------------------
     solve = {}
@@ -748,6 +764,9 @@ def run_ours(args) -> int:
             "h2d_bytes_per_step": X.numel() * 4 + V.numel() * 4,
             "d2h_bytes_per_step": n * k * 4,
             "steps": e2e_steps,
+            "checksum_abs_sum": e2e_checksum,
+            "result": "pinned host buffer" if world == 1 else
+                      "host buffer mapped and pinned by every rank; each rank delivers its row block over its own PCIe link",
         },
         "gpu_launches": launches,
         "roofline": roofline,

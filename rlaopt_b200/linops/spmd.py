@@ -95,10 +95,24 @@ class RowShardedLinOp(_BaseLinOp):
     def _matvec(self, x: torch.Tensor) -> torch.Tensor:
         return self._gather_rows(self.local_matmat(x))
 
+    def matmat_to_host(self, x: torch.Tensor, host_out: torch.Tensor, wait: bool = True) -> torch.Tensor:
+        """``A @ x`` delivered to host memory that every rank maps (``rlaopt_b200.utils.SharedPinnedTensor``): each
+        rank copies its own row block over its own PCIe link -- no gather on one GPU, no single-link funnel.  With
+        ``wait`` the call returns once all ranks' blocks have landed."""
+        vec = x.ndim == 1
+        loc = self.local_matmat(x)
+        if self.hi > self.lo:
+            dst = host_out[self.lo:self.hi]
+            dst.copy_(loc.reshape(dst.shape), non_blocking=True)
+        if wait:
+            torch.cuda.current_stream(self._device).synchronize() if self._device.type == "cuda" else None
+            dist.barrier(group=self.group)
+        return host_out[:, 0] if (vec and host_out.ndim == 2) else host_out
+
     # -- fused products (rlaopt_b200.linops.apply_fused) ---------------------
     def fused_reductions_ok(self, k: int, gram_cols: int = 0) -> bool:
-        ok = getattr(self.local_op, "fused_reductions_ok", None)
-        return bool(ok and ok(k, gram_cols)) if self.local_op is not None else (1 <= k <= 64 and gram_cols <= 64)
+        # must not depend on the rank (a rank without rows would otherwise take another collective path)
+        return True
 
     def matmat_fused(self, x: torch.Tensor, *, alpha=1.0, addend=None, beta=0.0, addend_idx=None, rhs=None, gamma=0.0,
                      rhs_idx=None, gram_with=None, want_sqnorm=False, store=True):
@@ -106,6 +120,8 @@ class RowShardedLinOp(_BaseLinOp):
         ``gram_with``); the row blocks are all-gathered and the k x k Gram partials and the column norms are
         all-reduced together in one small buffer -- the only reductions block PCG needs across ranks
         (``rlaopt/solvers/pcg.py:58-61``)."""
+        from .fused import apply_fused
+
         lo, hi = self.lo, self.hi
         k = 1 if x.ndim == 1 else x.shape[1]
         g = 0 if gram_with is None else (1 if gram_with.ndim == 1 else gram_with.shape[1])
@@ -118,17 +134,10 @@ class RowShardedLinOp(_BaseLinOp):
             return t, idx.to(t.device)[lo:hi]
 
         Y_loc = gram = sqn = None
-        if self.local_op is not None and hasattr(self.local_op, "matmat_fused"):
+        if self.local_op is not None:
             a_t, a_i = rows_of(addend, addend_idx)
             r_t, r_i = rows_of(rhs, rhs_idx)
-            Y_loc, gram, sqn = self.local_op.matmat_fused(
-                x, alpha=alpha, addend=a_t, beta=beta, addend_idx=a_i, rhs=r_t, gamma=gamma, rhs_idx=r_i,
-                gram_with=None if gram_with is None else gram_with[lo:hi], want_sqnorm=want_sqnorm, store=store)
-        elif self.local_op is not None:  # a local operator without a fused stage: separate passes on the block
-            from .fused import apply_fused
-
-            a_t, a_i = rows_of(addend, addend_idx)
-            r_t, r_i = rows_of(rhs, rhs_idx)
+            # the local operator's own fused stage when it has one (kernel operators), separate passes otherwise
             Y_loc, gram, sqn = apply_fused(
                 self.local_op, x, alpha=alpha, addend=a_t, beta=beta, addend_idx=a_i, rhs=r_t, gamma=gamma, rhs_idx=r_i,
                 gram_with=None if gram_with is None else gram_with[lo:hi], want_sqnorm=want_sqnorm, store=store)

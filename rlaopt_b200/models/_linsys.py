@@ -62,7 +62,8 @@ class Model:
             return solver.W, log
         for i in range(1, max_iters + 1):
             solver._step()
-            entry = logger._compute_log(i, solver.W)
+            # the iterate is only needed on logged iterations (a sharded solver assembles it on demand)
+            entry = logger._compute_log(i, solver.W) if i % logger.log_freq == 0 else None
             if entry is not None:
                 log[i] = entry
                 if termination_fn(entry["metrics"]["internal_metrics"]):
@@ -126,10 +127,10 @@ class LinSys(Model):
         the true residual by rounding, so convergence is *confirmed* once with the true residual before the solve
         stops; if the confirmation fails the solve continues on true residuals."""
         solver = getattr(self, "_solver", None)
-        R = getattr(solver, "R", None)
+        sqnorms = getattr(solver, "residual_sqnorms", None)
         self._metrics_from_recurrence = False
-        if self._residual_mode == "recurrence" and R is not None and solver.W is W:
-            abs_res = torch.linalg.norm(R, dim=0, ord=2)
+        if self._residual_mode == "recurrence" and sqnorms is not None and solver.W is W:
+            abs_res = sqnorms().sqrt()
             self._metrics_from_recurrence = True
         else:
             abs_res = self._true_sq_residual(W).sqrt()

@@ -46,6 +46,10 @@ class PCG(Solver):
         Y, G, _ = apply_fused(self.system.A, X, addend=X, beta=self.system.reg, gram_with=X if gram else None)
         return (Y, G) if gram else Y
 
+    def residual_sqnorms(self) -> torch.Tensor:
+        """Squared column norms of the recurrence residual (``LinSys.solve(..., residual="recurrence")``)."""
+        return (self.R * self.R).sum(dim=0)
+
     def _restart_from_residual(self, R: torch.Tensor) -> None:
         """Restart block CG at the current iterate from a freshly evaluated residual (``LinSys`` calls this when the
         true residual contradicts the recurrence): new preconditioned residual, steepest-descent directions, Gram."""
