@@ -515,11 +515,11 @@ def krr_pcg_c5(dev, n: int, sync_all) -> dict:
 
 def single_process_multi_gpu(n_dev: int) -> dict:
     """The reference-compatible constructor DistributedRBFLinOp(devices={cuda:0..N-1}) driven from ONE process
-    (rank 0 of the bench sees every GPU of the box): K(X[:65536], X) @ V at m = 1M, d = 128, k = 64, checked against
+    (rank 0 of the bench sees every GPU of the box): K(X[:37888 N], X) @ V at m = 1M, d = 128, k = 64, checked against
     fp64 rows computed on the device."""
     from rlaopt_b200.kernels import DistributedRBFLinOp, KernelConfig
 
-    n, m, d, k = 65_536, 1_000_000, 128, 64
+    n, m, d, k = 37_888 * n_dev, 1_000_000, 128, 64  # two full waves of 148 row blocks per device
     dev0 = torch.device("cuda", 0)
     g = torch.Generator(device=dev0).manual_seed(0)
     A2 = torch.randn(m, d, generator=g, device=dev0) / d**0.5

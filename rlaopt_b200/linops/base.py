@@ -164,11 +164,10 @@ class _BaseDistributedLinOp(_BaseLinOp):
         if self._closed:
             raise RuntimeError("distributed linear operator has been shut down")
         inputs: Sequence[torch.Tensor] = self._chunk_tensor(x, by_dimension) if chunk else [x] * len(self._A)
-        results = []
-        for op, dev, xi in zip(self._A, self._devices, inputs):
-            xi = xi.to(dev, non_blocking=True)
-            results.append(op @ xi if operation == _Operation.MATVEC else op.T @ xi)
-        return results
+        # all transfers first, then all products: a device-to-device copy is issued on the SOURCE device's stream, so
+        # a copy enqueued after that device's product would wait for it and serialise the devices
+        moved = [xi.to(dev, non_blocking=True) for dev, xi in zip(self._devices, inputs)]
+        return [op @ xi if operation == _Operation.MATVEC else op.T @ xi for op, xi in zip(self._A, moved)]
 
     @staticmethod
     def _combine_results(results: list[torch.Tensor], concatenate: bool, device: torch.device) -> torch.Tensor:
