@@ -14,7 +14,17 @@ from typing import Optional, Sequence
 import torch
 import torch.distributed as dist
 
-__all__ = ["SharedPinnedTensor"]
+__all__ = ["SharedPinnedTensor", "shared_host_available"]
+
+
+def shared_host_available(nbytes: int, limit_bytes: int = 4 << 30) -> bool:
+    """Whether ``/dev/shm`` can back ``nbytes`` of shared, page-locked memory (half of its free space at most, and
+    not more than ``limit_bytes``: registration of very large shared mappings fails on some hosts)."""
+    try:
+        st = os.statvfs("/dev/shm")
+    except OSError:
+        return False
+    return nbytes <= limit_bytes and nbytes <= (st.f_bavail * st.f_frsize) // 2
 
 
 class SharedPinnedTensor:

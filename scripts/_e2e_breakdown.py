@@ -17,7 +17,11 @@ n, d, k = 1_000_000, 128, 64
 g = torch.Generator().manual_seed(0)
 Xp = (torch.randn(n, d, generator=g) / d**0.5).pin_memory()
 Vp = torch.randn(n, k, generator=g).pin_memory()
-Yh = torch.empty(n, k).pin_memory()
+from rlaopt_b200 import ops
+from rlaopt_b200.utils import SharedPinnedTensor
+
+shared = SharedPinnedTensor("e2e_breakdown_Y", (n, k), torch.float32)
+Yh = shared.tensor
 cfg = KernelConfig(lengthscale=1.0)
 
 
@@ -29,22 +33,23 @@ def tick(label, t0, acc):
 
 
 acc = {}
-for step in range(4):
+for step in range(5):
     dist.barrier(); torch.cuda.synchronize(dev)
     t = time.perf_counter(); t_start = t
     Xg = replicate_from_host(Xp, dev); t = tick("replicate X (H2D 1/N + all-gather)", t, acc)
     op = sharded_kernel_linop(Xg, Xg, cfg, "rbf", dev); t = tick("operator construction", t, acc)
-    Vg = replicate_from_host(Vp, dev); t = tick("replicate V", t, acc)
-    Yl = op.local_op @ Vg if op.local_op is not None else None; t = tick("local block product (packs + kernel)", t, acc)
-    Y = op @ Vg; t = tick("second product incl. all-gather of Y (packs cached)", t, acc)
-    if rank == 0:
-        Yh.copy_(Y, non_blocking=True)
-    t = tick("D2H of Y (rank 0)", t, acc)
-    del op, Xg, Vg, Y, Yl
+    Vg = replicate_from_host(Vp, dev); t = tick("replicate V (H2D 1/N + all-gather)", t, acc)
+    c = op.local_op._cache.center(); t = tick("column means of X", t, acc)
+    P1, P2 = op.local_op._cache.get(ops.LAYOUT_TC); t = tick("pack row block + pack X", t, acc)
+    ok = op.local_op._cache.tc_ok(0); t = tick("norm statistics read-back", t, acc)
+    Yl = op.local_op @ Vg; t = tick("local block product (V pack + kernel)", t, acc)
+    Yh[op.lo:op.hi].copy_(Yl, non_blocking=True); t = tick("D2H of the row block (every rank, own link)", t, acc)
+    dist.barrier(); t = tick("barrier", t, acc)
+    del op, Xg, Vg, Yl, P1, P2
     t = tick("free", t, acc)
     acc.setdefault("whole step", []).append((t - t_start) * 1e3)
 if rank == 0:
     for key, v in acc.items():
         print(f"{key:55s} " + "  ".join(f"{x:8.1f}" for x in v) + "  ms")
-    print(torch.cuda.memory_summary(dev, abbreviated=True)[:1500])
+shared.close()
 dist.destroy_process_group()
