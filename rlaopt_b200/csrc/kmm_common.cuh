@@ -29,8 +29,15 @@ __host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + 
 
 template <typename T>
 __device__ __forceinline__ T pw_exp(T x);
+// fp32: exp(x) = ex2(x log2 e) with the hardware approximation (2^-22 relative error, one FMUL + one MUFU instead of
+// the ~8-instruction expf).  The product x log2 e is rounded once: |x| 2^-24 of relative error in the result, < 1e-6
+// for every argument whose exponential is not negligible in a sum of kernel values.
 template <>
-__device__ __forceinline__ float pw_exp<float>(float x) { return expf(x); }
+__device__ __forceinline__ float pw_exp<float>(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.44269504088896340736f));
+    return y;
+}
 template <>
 __device__ __forceinline__ double pw_exp<double>(double x) { return exp(x); }
 

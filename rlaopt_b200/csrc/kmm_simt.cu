@@ -11,6 +11,8 @@
 // columns contribute exactly 0.  Long column sums are accumulated in two levels
 // (registers for 1024 columns, then a thread-private smem slot) to keep fp32
 // round-off growth ~sqrt(1024) instead of ~sqrt(m).
+#include <stdlib.h>
+
 #include "kmm_common.cuh"
 #include "kmm_launch.h"
 
@@ -316,6 +318,186 @@ kmm_simt_kernel(const T* __restrict__ Rt, int64_t n, int64_t n_pad,
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// fp32, narrow k-chunks (instantiated for KC = 8; KC = 16 works but measured slower, see launch_kc): P stays in registers.
+//
+// Same 128 x 64 tile and the same phase 1 (8 x 8 distance tile per thread, 128 threads), but the thread that owns
+// P[8 rows][8 columns j] also contracts it: acc[8 rows][KC] += P[r][j] V[j][:] over ITS eight j.  The partial sums of
+// the eight threads that share a row block (the lanes tx = 0..7 of a row group) are added once, at the end of the
+// kernel, with three shuffles -- so the per-tile round trip of P through shared memory (64 stores + 64 loads per thread
+// and one barrier) is gone; what phase 2 reads from shared memory is V only (KC / 4 broadcast loads per 64 FFMA2).
+// V is staged as Vs[c / 4][perm(j)][4] with perm(j) = (j % 8) * 8 + j / 8: the eight lanes of a quarter-warp then read
+// eight consecutive 16-byte rows (conflict-free) although their columns j = 8 tx + cc are 8 apart.
+template <int KC>
+struct alignas(16) SimtRegpSmem {
+    float As[2][DC][BM];
+    float Bs[2][DC][BN];
+    float Vs[KC / 4][BN][4];
+    float Yt[8 * KC][BM];  // second-level accumulators, one private column per thread (128 threads)
+};
+
+template <bool L1, int KC>
+__global__ void __launch_bounds__(128, 2)
+kmm_simt_regp_kernel(const float* __restrict__ Rt, int64_t n, int64_t n_pad, const float* __restrict__ Ct, int64_t m,
+                     int64_t m_pad, int d_pad, const float* __restrict__ V, int64_t ldv, int k, int v_vec_ok,
+                     float* __restrict__ out, int64_t ldo, int64_t split_stride, float scale, int kid,
+                     int tiles_per_split) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SimtRegpSmem<KC>& sm = *reinterpret_cast<SimtRegpSmem<KC>*>(smem_raw);
+    constexpr int NT = 128, TN = 8, VEC = 4, NACC = 8 * KC;
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);  // 8 x 16 thread grid over the 64 x 128 tile
+    const int64_t row0 = (int64_t)blockIdx.x * BM;
+    const int kc0 = blockIdx.y * KC;
+    const int64_t n_col_tiles = (m + BN - 1) / BN;
+    const int64_t t_begin = (int64_t)blockIdx.z * tiles_per_split;
+    const int64_t t_end = min(n_col_tiles, t_begin + (int64_t)tiles_per_split);
+    const int nd = d_pad / DC;
+
+    auto load_ab = [&](int64_t t, int c, int buf) {
+        constexpr int A_CH = DC * BM / VEC;
+#pragma unroll
+        for (int q = tid; q < A_CH; q += NT) {
+            const int dd = q / (BM / VEC), i = (q % (BM / VEC)) * VEC;
+            cp_async16(&sm.As[buf][dd][i], Rt + (int64_t)(c * DC + dd) * n_pad + row0 + i);
+        }
+        constexpr int B_CH = DC * BN / VEC;
+        const int64_t col0 = t * BN;
+#pragma unroll
+        for (int q = tid; q < B_CH; q += NT) {
+            const int dd = q / (BN / VEC), j = (q % (BN / VEC)) * VEC;
+            cp_async16(&sm.Bs[buf][dd][j], Ct + (int64_t)(c * DC + dd) * m_pad + col0 + j);
+        }
+    };
+    auto load_v = [&](int64_t t) {
+        const int64_t col0 = t * BN;
+        constexpr int CH_PER_ROW = KC / VEC;
+        if (v_vec_ok) {
+#pragma unroll
+            for (int q = tid; q < BN * CH_PER_ROW; q += NT) {
+                const int j = q / CH_PER_ROW, c4 = q % CH_PER_ROW;
+                const int64_t gj = col0 + j;
+                const int gc = kc0 + c4 * VEC;
+                int valid = 0;
+                if (gj < m && gc < k) valid = min(VEC, k - gc) * (int)sizeof(float);
+                const float* src = valid ? V + gj * ldv + gc : V;
+                cp_async16(&sm.Vs[c4][(j % 8) * 8 + j / 8][0], src, valid);
+            }
+        } else {
+            for (int q = tid; q < BN * KC; q += NT) {
+                const int j = q / KC, c = q % KC;
+                const int64_t gj = col0 + j;
+                const int gc = kc0 + c;
+                sm.Vs[c / 4][(j % 8) * 8 + j / 8][c % 4] = (gj < m && gc < k) ? V[gj * ldv + gc] : 0.0f;
+            }
+        }
+    };
+
+    float acc[8][KC];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < KC; ++c) acc[r][c] = 0.0f;
+#pragma unroll
+    for (int e = 0; e < NACC; ++e) sm.Yt[e][tid] = 0.0f;
+
+    if (t_begin < t_end) {
+        load_ab(t_begin, 0, 0);
+        cp_async_commit();
+    }
+    int since_flush = 0;
+    for (int64_t t = t_begin; t < t_end; ++t) {
+        // ---------------- phase 1: distances (as kmm_simt_kernel) ----------------
+        float S[8][TN];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < TN; ++c) S[r][c] = 0.0f;
+        for (int c = 0; c < nd; ++c) {
+            cp_async_wait_all();
+            __syncthreads();  // chunk c landed; everyone is done with the other buffer and (c == 0) with Vs
+            if (c == 0) load_v(t);
+            if (c + 1 < nd) load_ab(t, c + 1, (c + 1) & 1);
+            cp_async_commit();
+            const int buf = c & 1;
+#pragma unroll 1
+            for (int dd = 0; dd < DC; ++dd) {
+                alignas(16) float a[8];
+                alignas(16) float b[TN];
+                lds_vec<float, 8>(a, &sm.As[buf][dd][ty * 8]);
+                lds_vec<float, TN>(b, &sm.Bs[buf][dd][tx * TN]);
+                uint64_t bp[TN / 2];
+#pragma unroll
+                for (int c2 = 0; c2 < TN / 2; ++c2) bp[c2] = pk2(b[2 * c2], b[2 * c2 + 1]);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint64_t ar = pk2(a[r], a[r]);
+#pragma unroll
+                    for (int c2 = 0; c2 < TN / 2; ++c2) {
+                        const uint64_t diff = sub2(ar, bp[c2]);
+                        if constexpr (L1) {
+                            float lo, hi;
+                            up2(diff, lo, hi);
+                            S[r][2 * c2] += fabsf(lo);
+                            S[r][2 * c2 + 1] += fabsf(hi);
+                        } else {
+                            up2(fma2(diff, diff, pk2(S[r][2 * c2], S[r][2 * c2 + 1])), S[r][2 * c2], S[r][2 * c2 + 1]);
+                        }
+                    }
+                }
+            }
+        }
+        // ---------------- pointwise in place: P = f(S) ----------------
+        pointwise_tile<float, 8, TN>(kid, S);
+        cp_async_wait_all();
+        __syncthreads();  // V landed; As / Bs are free
+        if (t + 1 < t_end) {
+            load_ab(t + 1, 0, 0);
+            cp_async_commit();
+        }
+        // ---------------- phase 2: acc[r][:] += P[r][cc] V[8 tx + cc][:], P from registers ----------------
+#pragma unroll
+        for (int cc = 0; cc < TN; ++cc) {
+#pragma unroll
+            for (int c4 = 0; c4 < KC / 4; ++c4) {
+                const float4 v = *reinterpret_cast<const float4*>(&sm.Vs[c4][cc * 8 + tx][0]);
+                const uint64_t v01 = pk2(v.x, v.y), v23 = pk2(v.z, v.w);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint64_t pr = pk2(S[r][cc], S[r][cc]);
+                    up2(fma2(pr, v01, pk2(acc[r][4 * c4], acc[r][4 * c4 + 1])), acc[r][4 * c4], acc[r][4 * c4 + 1]);
+                    up2(fma2(pr, v23, pk2(acc[r][4 * c4 + 2], acc[r][4 * c4 + 3])), acc[r][4 * c4 + 2], acc[r][4 * c4 + 3]);
+                }
+            }
+        }
+        if (++since_flush == FLUSH_TILES) {
+            since_flush = 0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < KC; ++c) {
+                    sm.Yt[r * KC + c][tid] += acc[r][c];
+                    acc[r][c] = 0.0f;
+                }
+        }
+    }
+    // ---------------- row sums over the eight lanes that share a row group, then one writer per group ----------------
+    float* dst = out + (int64_t)blockIdx.z * split_stride;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int64_t i = row0 + ty * 8 + r;
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+            float y = sm.Yt[r * KC + c][tid] + acc[r][c];
+            y += __shfl_xor_sync(0xffffffffu, y, 1);
+            y += __shfl_xor_sync(0xffffffffu, y, 2);
+            y += __shfl_xor_sync(0xffffffffu, y, 4);
+            const int col = kc0 + c;
+            if (tx == 0 && i < n && col < k) dst[i * ldo + col] = y * scale;
+        }
+    }
+}
+
 template <typename T>
 __global__ void kmm_split_reduce_kernel(const T* __restrict__ part, int splits, int64_t nk, int64_t k,
                                         T* __restrict__ Y, int64_t ldy, T scale) {
@@ -344,9 +526,42 @@ cudaError_t launch_one(const SimtArgs<T>& a, int splits, int tiles_per_split, T*
     return cudaGetLastError();
 }
 
+// fp32 with at most 8 columns per chunk: the register-resident-P kernel (RLAOPT_B200_SIMT_REGP=0 keeps the
+// shared-memory P kernel, for A/B runs)
+template <bool L1, int KC>
+cudaError_t launch_regp(const SimtArgs<float>& a, int splits, int tiles_per_split, float* out, int64_t ldo,
+                        int64_t split_stride, float scale) {
+    using Smem = SimtRegpSmem<KC>;
+    auto kern = kmm_simt_regp_kernel<L1, KC>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (err != cudaSuccess) return err;
+    const int64_t row_tiles = (a.n + BM - 1) / BM;
+    const int k_chunks = (int)((a.k + KC - 1) / KC);
+    dim3 grid((unsigned)row_tiles, (unsigned)k_chunks, (unsigned)splits);
+    const int v_vec_ok = ((reinterpret_cast<uintptr_t>(a.V) % 16) == 0) && ((a.ldv * sizeof(float)) % 16 == 0);
+    kern<<<grid, 128, sizeof(Smem), a.stream>>>(a.Rt, a.n, a.n_pad, a.Ct, a.m, a.m_pad, (int)a.d_pad, a.V, a.ldv, (int)a.k,
+                                                v_vec_ok, out, ldo, split_stride, scale, a.kid, tiles_per_split);
+    return cudaGetLastError();
+}
+
+bool simt_regp_enabled() {
+    static const int on = [] {
+        const char* v = getenv("RLAOPT_B200_SIMT_REGP");
+        return (v && *v) ? atoi(v) : 1;
+    }();
+    return on != 0;
+}
+
 template <typename T, bool L1>
 cudaError_t launch_kc(const SimtArgs<T>& a, int kc, int splits, int tiles_per_split, T* out, int64_t ldo,
                       int64_t split_stride, T scale) {
+    if constexpr (sizeof(T) == 4) {
+        // measured (profiles/r02_simt_regp_ab.log): +3 % for chunks of 8 columns (Laplace d=32 k=8 359 -> 372, d=8 k=10
+        // 633 -> 650 Gentries/s); with 16 columns the 128 accumulators cost a third of the resident warps and the
+        // shared-memory-P kernel stays ahead (332 vs 320), so only KC = 8 runs here
+        if (simt_regp_enabled() && kc == 8)
+            return launch_regp<L1, 8>(a, splits, tiles_per_split, out, ldo, split_stride, scale);
+    }
     switch (kc) {
         case 8: return launch_one<T, L1, 8>(a, splits, tiles_per_split, out, ldo, split_stride, scale);
         case 16: return launch_one<T, L1, 16>(a, splits, tiles_per_split, out, ldo, split_stride, scale);

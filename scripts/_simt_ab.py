@@ -10,14 +10,17 @@ from rlaopt_b200.kernels import KernelConfig
 
 dev = torch.device("cuda:0")
 CASES = [  # (class, dtype, n, m, d, k)
+    ("LaplaceLinOp", torch.float32, 113664, 1 << 21, 32, 16),
     ("LaplaceLinOp", torch.float32, 65536, 1 << 20, 32, 16),
+    ("LaplaceLinOp", torch.float32, 65536, 1 << 20, 32, 8),
+    ("LaplaceLinOp", torch.float32, 65536, 1 << 20, 8, 10),
     ("LaplaceLinOp", torch.float32, 32768, 1 << 19, 128, 64),
     ("LaplaceLinOp", torch.float32, 65536, 1 << 20, 16, 1),
     ("RBFLinOp", torch.float32, 65536, 1 << 20, 32, 16),
     ("Matern52LinOp", torch.float32, 32768, 1 << 19, 128, 64),
     ("LaplaceLinOp", torch.float64, 16384, 1 << 18, 32, 16),
 ]
-print("lib:", os.environ.get("RLAOPT_B200_LIB", "default"))
+print("lib:", os.environ.get("RLAOPT_B200_LIB", "default"), "regp:", os.environ.get("RLAOPT_B200_SIMT_REGP", "1"))
 for name, dt, n, m, d, k in CASES:
     g = torch.Generator().manual_seed(0)
     A1 = (torch.randn(n, d, generator=g, dtype=dt) / d**0.5).to(dev)
