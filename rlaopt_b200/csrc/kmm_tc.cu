@@ -183,6 +183,32 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// ---- cta_group::2 (CTA pair issuing one MMA over both SMs; every tcgen05 instruction of such a kernel carries it) ----
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// arrives on the barrier at this smem offset in every CTA of `mask` once all MMAs issued so far by this thread are done
+__device__ __forceinline__ void umma_commit2_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(rank)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -203,10 +229,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
 }
-// instruction descriptor: fp32 accumulate, K-major A and B, M = 128
-__host__ __device__ constexpr uint32_t umma_idesc(int ab_format, int n) {
+// instruction descriptor: fp32 accumulate, K-major A and B, M = 128 (256 for a cta_group::2 MMA over a CTA pair)
+__host__ __device__ constexpr uint32_t umma_idesc(int ab_format, int n, int m = TC_BM) {
     return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(TC_BM >> 4) << 24);
+           ((uint32_t)(m >> 4) << 24);
 }
 constexpr int FMT_F16 = 0;
 
@@ -382,11 +408,16 @@ __global__ void tc_pack_points_kernel(const float* __restrict__ X, int64_t n, in
     if ((threadIdx.x & 31) == 0 && wmax > 0.0f) atomicMax(&hdr->max_sqnorm_bits, __float_as_uint(wmax));
 }
 
+// bytes of one V record in the workspace: fp16 image (hi | lo), 16 B trailer {1 / s}, 64 column norms
+__host__ __device__ constexpr size_t tc_v_record_bytes(int kp) { return (size_t)kp * 256 + 16 + TC_BN * 4; }
+
 // V[m][k] -> per (k-chunk, 64-row sub-tile) image of the MMA2 B operand, one block per image:
 //   [hi | lo] x [row c of KP] x 128 B (64 j as fp16, 16 B chunks XOR-swizzled by c & 7) | 16 B trailer {1/s}
 // The tile is scaled by a power of two s (|v s| in [2^14, 2^15)) before the fp16 hi/lo split, so
 // the pair keeps 22 significant bits of every element within 2^-29 of the tile maximum.
+//   | 64 squared column norms (copied from the packed column operand): one record = one bulk copy per V-ring stage
 __global__ void __launch_bounds__(256) tc_pack_v_kernel(const float* __restrict__ V, int64_t m, int64_t k, int64_t ldv,
+                                                        const float* __restrict__ col_norms,
                                                         unsigned char* __restrict__ images, int kp, int64_t sub_tiles) {
     extern __shared__ float vt[];  // [64][kp + 1]
     __shared__ float red[8];
@@ -413,8 +444,10 @@ __global__ void __launch_bounds__(256) tc_pack_v_kernel(const float* __restrict_
     if (mx > 0.0f) E = 14 - ilogbf(mx);
     E = max(-126, min(126, E));
     const float s = __uint_as_float((uint32_t)(127 + E) << 23);
-    const size_t image_bytes = (size_t)kp * 256 + 16;
+    const size_t image_bytes = tc_v_record_bytes(kp);
     unsigned char* img = images + ((size_t)kc * sub_tiles + t) * image_bytes;
+    if (tid < TC_BN)  // the packed operand holds norms for all padded points
+        reinterpret_cast<float*>(img + (size_t)kp * 256 + 16)[tid] = col_norms[t * TC_BN + tid];
     for (int ch = tid; ch < kp * 8; ch += 256) {
         const int c = ch >> 3, q8 = ch & 7;
         alignas(16) __half hi[8];
@@ -519,6 +552,22 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32
         : "memory");
 }
 
+// the same MMA issued by the leader CTA of a pair for both SMs: D and A at the same TMEM address in each CTA, B split
+// along N between the two CTAs' shared memory (each holds its N / 2 rows at the descriptor's offset)
+__device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi,
+                                         uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 bd;\n"
+        "mov.b64 bd, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], bd, %4, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
 template <int N>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
     if constexpr (N == 32) tmem_ld32(taddr, r);
@@ -558,9 +607,15 @@ __host__ __device__ constexpr uint32_t tc_v_stage_bytes(int kp) { return (uint32
 // epilogue thread that owns a row multiplies its 64 kernel values with the raw fp32 V tile from the V ring.
 // KIDT >= 0: kernel id fixed at compile time (register-contraction instantiations: the fully unrolled epilogue is
 // sensitive to its instruction footprint, so it carries the code of one kernel function only)
-template <int KP, int NWG, bool M12, bool WIDE, int KV = 0, int KIDT = -1>
+// CG2: CTA pair with cta_group::2 MMAs (k > 64 family).  The leader CTA (cluster rank 0) issues MMA1 and MMA2 for both
+// SMs (M = 256: each SM computes its own 128 rows); every CTA loads only HALF of each column-tile image and of each V
+// image (its N / 2 rows of the B operand) into its own shared memory -- the per-SM ingress that bounds this family
+// (48 KB per 1152 tensor cycles = 42 B/clk, the L2 -> SM limit) is halved.  The peer's epilogue warps arrive on the
+// leader's barriers through the cluster window; two of its idle issue warps relay its "tile landed" barriers.
+template <int KP, int NWG, bool M12, bool WIDE, int KV = 0, int KIDT = -1, bool CG2 = false>
 __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcParams p) {
     static_assert(KV == 0 || (KV <= 4 && KP == 16 && !WIDE), "register contraction: k <= 4, X resident in TMEM");
+    static_assert(!CG2 || (KP == 128 && !WIDE && KV == 0 && NWG == 2), "cta_group::2 is built for the k > 64 family");
     constexpr int TC_EPI_WARPS = NWG * 4;
     constexpr int NOB = NWG;  // O buffers: one per epilogue warpgroup (tile u accumulates into O[u % NWG])
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -569,7 +624,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     const uint32_t a_img_bytes = (uint32_t)tc_image_bytes(KB);  // hi + lo image of one 64-point tile in HBM
     const uint32_t a_stage_bytes = WIDE ? TC_WIDE_STAGE_BYTES : a_img_bytes;  // one slot of the A ring
     // V tile as stored in HBM: fp16 image hi + lo + trailer, or (KV) the raw fp32 tile [KV][64]
-    constexpr uint32_t v_img_bytes = KV ? (KV + 1) * 256 : KP * 256 + 16;  // KV: the record ends with the 64 column norms
+    constexpr uint32_t v_img_bytes = KV ? (KV + 1) * 256 : KP * 256 + 16 + TC_BN * 4;  // the record ends with the 64 column norms
     constexpr uint32_t v_stage_bytes = tc_v_stage_bytes(KP);
     constexpr uint32_t v_norm_off = KV ? KV * 256 : KP * 256 + 16;
     unsigned char* a_ring = smem;
@@ -586,7 +641,9 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     uint64_t* o_full = p_free + NB;      // [NOB] O buffer complete
     uint64_t* o_free = o_full + NOB;     // [NOB] O buffer drained
     uint64_t* x_full = o_free + NOB;     // [1] X tile resident in TMEM (8 warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 1);
+    uint64_t* a_peer = x_full + 1;       // [SA] CG2, leader: the peer's half of the column-tile image has landed
+    uint64_t* v_peer = a_peer + SA;      // [SV] CG2, leader: the peer's half of the V image has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_peer + SV);
 
     const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
     const int kc = blockIdx.y;
@@ -595,28 +652,35 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     const int T = (int)(t_end - t_begin);
 
     if (threadIdx.x == 0) {
-        const uint32_t consumers = p.pair ? 2 : 1;  // a ring slot is free once both CTAs of the pair have read it
+        // multicast pairs: a ring slot is free once both CTAs of the pair have read it; CG2: one MMA reads both halves
+        const uint32_t consumers = (p.pair && !CG2) ? 2 : 1;
+        const uint32_t ctas = CG2 ? 2 : 1;  // CG2: the peer's epilogue warps arrive on the leader's barriers too
         for (int s = 0; s < SA; ++s) {
             mbar_init(&a_full[s], 1);
             mbar_init(&a_empty[s], consumers);
+            mbar_init(&a_peer[s], 1);
         }
         for (int s = 0; s < SV; ++s) {
             mbar_init(&v_full[s], 1);
             mbar_init(&v_empty[s], KV ? 4 : consumers);  // KV: released by the four warps that read the stage
+            mbar_init(&v_peer[s], 1);
         }
         for (int b = 0; b < NB; ++b) {
             mbar_init(&s_full[b], 1);
-            mbar_init(&p_full[b], 4);  // the four warps of the owning warpgroup
+            mbar_init(&p_full[b], 4 * ctas);  // the four warps of the owning warpgroup
             mbar_init(&p_free[b], KV ? 4 : 1);  // KV: S[b] is free once its four warps hold it in registers
         }
         for (int b = 0; b < NOB; ++b) {
             mbar_init(&o_full[b], 1);
-            mbar_init(&o_free[b], KP > 64 ? 8 : 4);
+            mbar_init(&o_free[b], (KP > 64 ? 8 : 4) * ctas);
         }
-        mbar_init(x_full, 8);  // warpgroups 0 and 1 load the X tile
+        mbar_init(x_full, 8 * ctas);  // warpgroups 0 and 1 load the X tile
         fence_barrier_init();
     }
-    if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, 512);
+    if (warp == TC_EPI_WARPS) {
+        if constexpr (CG2) tmem_alloc2(tmem_slot, 512);
+        else tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
     __syncthreads();
     if (p.pair) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
@@ -624,6 +688,13 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     const uint32_t tmem = *tmem_slot;
     const uint32_t x_cols = WIDE ? 0 : KB * 64;  // wide-d: X is not resident in TMEM
     const uint32_t col_a_hi = 0, col_a_lo = KB * 32, col_sp = x_cols, col_o = x_cols + NB * 64;
+
+    // CG2: barriers the leader's issue warps wait on collect arrivals from both CTAs (cluster-scope arrive on rank 0)
+    auto arrive_pair = [&](uint64_t* bar) {
+        if constexpr (CG2) mbar_arrive_cluster(bar, 0);
+        else mbar_arrive(bar);
+    };
+    const uint32_t crank2 = CG2 ? cluster_ctarank() : 0;
 
     const TcHeader* rh = reinterpret_cast<const TcHeader*>(p.rows);
     const TcHeader* ch = reinterpret_cast<const TcHeader*>(p.cols);
@@ -639,7 +710,6 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         if (lane == 0) {
             const unsigned char* a_src = col_images + (size_t)t_begin * a_img_bytes;
             const unsigned char* v_src = p.vimg + ((size_t)kc * p.sub_tiles + t_begin) * v_img_bytes;
-            const float* n_src = col_norms + t_begin * TC_BN;
             int sa = 0, sv = 0;
             uint32_t pha = 1, phv = 1;  // a fresh barrier passes a wait on parity 1
             const uint32_t crank = p.pair ? cluster_ctarank() : 0;
@@ -683,18 +753,15 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                     for (int e = 0; e < cnt; ++e) {
                         mbar_wait(&v_empty[sv], phv);
                         unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
-                        mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
+                        mbar_arrive_expect_tx(&v_full[sv], v_img_bytes);
                         if (!p.pair) {
                             bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
-                            bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
                         } else if (crank == 0) {
                             bulk_copy_g2s_mc(vdst, v_src, KP * 128, &v_full[sv], 3);
-                            bulk_copy_g2s_mc(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv], 3);
                         } else {
-                            bulk_copy_g2s_mc(vdst + KP * 128, v_src + KP * 128, KP * 128 + 16, &v_full[sv], 3);
+                            bulk_copy_g2s_mc(vdst + KP * 128, v_src + KP * 128, v_img_bytes - KP * 128, &v_full[sv], 3);
                         }
                         v_src += v_img_bytes;
-                        n_src += TC_BN;
                         if (++sv == SV) {
                             sv = 0;
                             phv ^= 1;
@@ -715,14 +782,31 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                     // issuing both rings is the bottleneck
                     mbar_arrive_expect_tx(&a_full[sa], a_img_bytes);
                     bulk_copy_g2s(a_ring + (size_t)sa * a_img_bytes, a_src, a_img_bytes, &a_full[sa]);
+                } else if constexpr (CG2) {
+                    // this CTA's half of the B operands, into its own shared memory: points [32 r, 32 r + 32) of every
+                    // K-block of the column tile (hi and lo), rows [64 r, 64 r + 64) of the V image (hi and lo), and
+                    // the whole trailer + column norms (both CTAs' epilogues read them)
+                    unsigned char* adst = a_ring + (size_t)sa * a_img_bytes;
+                    mbar_arrive_expect_tx(&a_full[sa], a_img_bytes / 2);
+                    for (int part = 0; part < 2; ++part)
+                        for (int kb = 0; kb < KB; ++kb)
+                            bulk_copy_g2s(adst + (size_t)(part * KB + kb) * (TC_KBLOCK_BYTES / 2),
+                                          a_src + (size_t)(part * KB + kb) * TC_KBLOCK_BYTES + crank * (TC_KBLOCK_BYTES / 2),
+                                          TC_KBLOCK_BYTES / 2, &a_full[sa]);
+                    mbar_wait(&v_empty[sv], phv);
+                    unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
+                    constexpr uint32_t v_q = KP * 64;  // half of the hi (or lo) image: 64 rows x 128 B
+                    mbar_arrive_expect_tx(&v_full[sv], 2 * v_q + 16 + TC_BN * 4);
+                    bulk_copy_g2s(vdst, v_src + crank * v_q, v_q, &v_full[sv]);
+                    bulk_copy_g2s(vdst + v_q, v_src + KP * 128 + crank * v_q, v_q, &v_full[sv]);
+                    bulk_copy_g2s(vdst + KP * 256, v_src + KP * 256, 16 + TC_BN * 4, &v_full[sv]);
                 } else if (!p.pair) {
                     mbar_arrive_expect_tx(&a_full[sa], a_img_bytes);
                     bulk_copy_g2s(a_ring + (size_t)sa * a_img_bytes, a_src, a_img_bytes, &a_full[sa]);
                     mbar_wait(&v_empty[sv], phv);
                     unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
-                    mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
-                    bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);
-                    bulk_copy_g2s(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv]);
+                    mbar_arrive_expect_tx(&v_full[sv], v_img_bytes);
+                    bulk_copy_g2s(vdst, v_src, v_img_bytes, &v_full[sv]);  // image, 1 / s_V and column norms: one record
                 } else {
                     // each CTA of the pair fetches half of every image and multicasts it to both
                     const uint32_t a_half = a_img_bytes / 2;
@@ -731,19 +815,17 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                                      &a_full[sa], 3);
                     mbar_wait(&v_empty[sv], phv);
                     unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
-                    mbar_arrive_expect_tx(&v_full[sv], v_img_bytes + TC_BN * 4);
+                    mbar_arrive_expect_tx(&v_full[sv], v_img_bytes);
                     constexpr uint32_t v_half = KP * 128;
                     if (crank == 0) {
                         bulk_copy_g2s_mc(vdst, v_src, v_half, &v_full[sv], 3);
-                        bulk_copy_g2s_mc(vdst + v_norm_off, n_src, TC_BN * 4, &v_full[sv], 3);
                     } else {
-                        bulk_copy_g2s_mc(vdst + v_half, v_src + v_half, v_half + 16, &v_full[sv], 3);
+                        bulk_copy_g2s_mc(vdst + v_half, v_src + v_half, v_img_bytes - v_half, &v_full[sv], 3);
                     }
                 }
                 }
                 a_src += a_img_bytes;
                 v_src += v_img_bytes;
-                n_src += TC_BN;
                 if (++sa == SA) {
                     sa = 0;
                     pha ^= 1;
@@ -759,13 +841,25 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         // The whole warp runs the (warp-uniform) control flow so addresses live in uniform
         // registers; one elected lane issues the tcgen05 instructions.  The MMA1 issuers run ahead of
         // MMA2 as far as the NB S/P buffers allow, so neither MMA waits for the other's completion.
-        constexpr uint32_t idesc1 = umma_idesc(FMT_F16, TC_BN);
-        constexpr uint32_t idesc2 = umma_idesc(FMT_F16, KP);
+        constexpr uint32_t idesc1 = umma_idesc(FMT_F16, TC_BN, CG2 ? 2 * TC_BM : TC_BM);
+        constexpr uint32_t idesc2 = umma_idesc(FMT_F16, KP, CG2 ? 2 * TC_BM : TC_BM);
+        // CG2: a CTA's slot holds its half of each K-block (32 points x 128 B) and of each V image (64 rows x 128 B)
+        constexpr uint32_t kblock_bytes = CG2 ? TC_KBLOCK_BYTES / 2 : TC_KBLOCK_BYTES;
+        constexpr uint32_t v_lo_off = CG2 ? KP * 64 : KP * 128;
+        auto mma_ts = [](uint32_t d_t, uint32_t a_t, uint32_t dlo, uint32_t dhi, uint32_t idesc, uint32_t acc) {
+            if constexpr (CG2) umma_ts2(d_t, a_t, dlo, dhi, idesc, acc);
+            else umma_ts(d_t, a_t, dlo, dhi, idesc, acc);
+        };
+        auto commit_bar = [&](uint64_t* bar, bool shared_slot) {  // shared_slot: a ring slot both CTAs of a pair read
+            if constexpr (CG2) umma_commit2_mc(bar, 3);
+            else if (shared_slot && p.pair) umma_commit_mc(bar, 3);
+            else umma_commit(bar);
+        };
         const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
         const uint32_t desc_lo0 = (uint32_t)(umma_desc_sw128(0) & 0xFFFFFFFFu);
         const int nk1 = p.nk1;
         const uint32_t a_ring_base = smem_u32(a_ring), v_ring_base = smem_u32(v_ring);
-        const uint32_t lo_off = (uint32_t)KB * TC_KBLOCK_BYTES;
+        const uint32_t lo_off = (uint32_t)KB * kblock_bytes;
 
         // S[b] = X . Y_tile^T : hi.lo + lo.hi + hi.hi, one K = 16 step per instruction
         auto issue_mma1 = [&](int b, int s) {
@@ -782,16 +876,16 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                     int ks = 0;
 #pragma unroll 1
                     for (; ks + 4 <= nk1; ks += 4) {  // one 64-wide K-block: 4 steps of 32 B inside the 128 B row
-                        umma_ts(d_t, a, bd, desc_hi, idesc1, acc);
-                        umma_ts(d_t, a + 8, bd + 2, desc_hi, idesc1, 1);
-                        umma_ts(d_t, a + 16, bd + 4, desc_hi, idesc1, 1);
-                        umma_ts(d_t, a + 24, bd + 6, desc_hi, idesc1, 1);
+                        mma_ts(d_t, a, bd, desc_hi, idesc1, acc);
+                        mma_ts(d_t, a + 8, bd + 2, desc_hi, idesc1, 1);
+                        mma_ts(d_t, a + 16, bd + 4, desc_hi, idesc1, 1);
+                        mma_ts(d_t, a + 24, bd + 6, desc_hi, idesc1, 1);
                         acc = 1;
                         a += 32;
-                        bd += TC_KBLOCK_BYTES >> 4;
+                        bd += kblock_bytes >> 4;
                     }
                     for (; ks < nk1; ++ks) {
-                        umma_ts(d_t, a, bd, desc_hi, idesc1, acc);
+                        mma_ts(d_t, a, bd, desc_hi, idesc1, acc);
                         acc = 1;
                         a += 8;
                         bd += 2;
@@ -806,7 +900,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             const uint32_t p_hi = tmem + col_sp + b * 64, p_lo = p_hi + 32;
             const uint32_t img = v_ring_base + (uint32_t)s * v_stage_bytes;
             const uint32_t dlo_hi = desc_lo0 + (img >> 4);
-            const uint32_t dlo_lo = desc_lo0 + ((img + KP * 128) >> 4);
+            const uint32_t dlo_lo = desc_lo0 + ((img + v_lo_off) >> 4);
             if (!TC_DIAG(1) && elect_one()) {
 #pragma unroll
                 for (int part = 0; part < 3; ++part) {
@@ -814,7 +908,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                     const uint32_t bd = (part == 0 ? dlo_lo : dlo_hi);
 #pragma unroll
                     for (int ks = 0; ks < TC_BN / 16; ++ks) {
-                        umma_ts(d_t, a + ks * 8, bd + ks * 2, desc_hi, idesc2, (part | ks) != 0);
+                        mma_ts(d_t, a + ks * 8, bd + ks * 2, desc_hi, idesc2, (part | ks) != 0);
                     }
                 }
             }
@@ -873,6 +967,22 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                         __syncwarp();
                     }
                 }
+            } else if (CG2 && crank2 != 0) {
+                // ---- peer CTA of a cta_group::2 pair: no MMA is issued here; warp 9 tells the leader when this CTA's
+                // half of a column-tile image has landed ----
+                if (par == 0) {
+                    int sa = 0;
+                    uint32_t pha = 0;
+                    for (int t1 = 0; t1 < T; ++t1) {
+                        mbar_wait(&a_full[sa], pha);
+                        if (lane == 0) mbar_arrive_cluster(&a_peer[sa], 0);
+                        __syncwarp();
+                        if (++sa == SA) {
+                            sa = 0;
+                            pha ^= 1;
+                        }
+                    }
+                }
             } else {
             mbar_wait(x_full, 0);
             int b1 = par % NB, sa = par % SA;
@@ -880,15 +990,15 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             TC_PROF_DECL
             for (int t1 = par; t1 < T; t1 += 2) {
                 TC_PROF(7)
-                // A image landed; MMA2 of tile t1 - NB has consumed P[b1]
-                mbar_wait2(&a_full[sa], pha, &p_free[b1], use1 ^ 1);
+                // A image landed (CG2: in both CTAs); MMA2 of tile t1 - NB has consumed P[b1]
+                if constexpr (CG2) mbar_wait3(&a_full[sa], pha, &a_peer[sa], pha, &p_free[b1], use1 ^ 1);
+                else mbar_wait2(&a_full[sa], pha, &p_free[b1], use1 ^ 1);
                 TC_PROF(0)
                 tc_fence_after();
                 issue_mma1(b1, sa);
                 if (elect_one()) {
-                    umma_commit(&s_full[b1]);
-                    if (p.pair) umma_commit_mc(&a_empty[sa], 3);
-                    else umma_commit(&a_empty[sa]);
+                    commit_bar(&s_full[b1], false);
+                    commit_bar(&a_empty[sa], true);
                 }
                 __syncwarp();
                 TC_PROF(2)
@@ -924,6 +1034,19 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                         }
                     }
                 }
+            } else if (CG2 && crank2 != 0) {
+                // ---- peer CTA: relay "this CTA's half of the V image has landed" to the leader ----
+                int sv = 0;
+                uint32_t phv = 0;
+                for (int u = 0; u < T; ++u) {
+                    mbar_wait(&v_full[sv], phv);
+                    if (lane == 0) mbar_arrive_cluster(&v_peer[sv], 0);
+                    __syncwarp();
+                    if (++sv == SV) {
+                        sv = 0;
+                        phv ^= 1;
+                    }
+                }
             } else {
             int b2 = 0, sv = 0;
             uint32_t use2 = 0, phv = 0;
@@ -932,16 +1055,16 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                 const int ob = u % NOB;
                 const uint32_t opar = (uint32_t)((u / NOB) & 1);  // use-count parity of O[ob]
                 TC_PROF(7)
-                // P written; V image landed; O[ob] of tile u - 2 has been drained
+                // P written; V image landed; O[ob] of tile u - 2 has been drained (CG2: in both CTAs)
+                if constexpr (CG2) mbar_wait(&v_peer[sv], phv);
                 mbar_wait3(&p_full[b2], use2, &v_full[sv], phv, &o_free[ob], opar ^ 1);
                 TC_PROF(3)
                 tc_fence_after();
                 issue_mma2(b2, ob, sv);
                 if (elect_one()) {
-                    if (p.pair) umma_commit_mc(&v_empty[sv], 3);
-                    else umma_commit(&v_empty[sv]);
-                    umma_commit(&p_free[b2]);
-                    umma_commit(&o_full[ob]);
+                    commit_bar(&v_empty[sv], true);
+                    commit_bar(&p_free[b2], false);
+                    commit_bar(&o_full[ob], false);
                 }
                 __syncwarp();
                 TC_PROF(6)
@@ -994,7 +1117,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(x_full);
+            if (lane == 0) arrive_pair(x_full);
         }
 
         // Two warpgroups ping-pong over the sub-tiles (warpgroup g owns tiles u = g, g+2, ...): each
@@ -1013,9 +1136,10 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         for (int c = 0; c < DW / 2; ++c) acc[c] = 0ull;
 
         // acc += O[ob] * dsc: one sub-tile's accumulator, un-scaled and added with round-to-nearest
-        auto drain = [&](int ob, uint32_t par, float dsc) {
+        auto drain = [&](int ob, uint32_t par, float dsc, const float* dsc_ptr = nullptr) {
             mbar_wait(&o_full[ob], par);
             tc_fence_after();
+            if (dsc_ptr) dsc = *dsc_ptr;
             const uint64_t d2 = pack2(dsc, dsc);
             constexpr int W = DW < 32 ? DW : 32;
             constexpr int NLD = DW / W;  // 1 or 2 loads in flight, one wait (a tcgen05.ld round trip is ~180 cycles)
@@ -1032,15 +1156,16 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                                                 acc[l * (W / 2) + e]);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&o_free[ob]);
+            if (lane == 0) arrive_pair(&o_free[ob]);
         };
         float* dsc_sm = xchg;  // [8][128]: per-row un-scale factors of the last 8 tiles (SPLIT mode)
         int next_drain = 0;    // SPLIT mode: next tile this warpgroup has to drain
         auto drain_through = [&](int last) {  // SPLIT mode: drain tiles next_drain .. last (inclusive)
             for (; next_drain <= last; ++next_drain) {
                 const int t = next_drain;
-                mbar_wait(&o_full[t % NOB], (uint32_t)((t / NOB) & 1));  // also orders the read of the owner's scale
-                drain(t % NOB, (uint32_t)((t / NOB) & 1), dsc_sm[(t & 7) * TC_BM + row]);
+                // the owner's scale is read inside drain(), after its wait on o_full (published before p_full ->
+                // MMA2 -> o_full): one barrier poll per drain, not two (a successful poll costs ~100 cycles)
+                drain(t % NOB, (uint32_t)((t / NOB) & 1), -1.0f, &dsc_sm[(t & 7) * TC_BM + row]);
             }
         };
 
@@ -1411,7 +1536,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             tc_fence_before();
             if (SPLIT) dsc_sm[(u & 7) * TC_BM + row] = dsc;  // published before p_full -> MMA2 -> o_full
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[b]);
+            if (lane == 0) arrive_pair(&p_full[b]);
             TC_PROF(4)
             // drain finished sub-tiles while the tensor core works on this one
             if (SPLIT) drain_through(u - 1);
@@ -1535,11 +1660,14 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     tc_fence_before();
     __syncthreads();
     if (p.pair) cluster_sync_all();  // no CTA leaves while its peer can still multicast into it or signal its barriers
-    if (warp == TC_EPI_WARPS) tmem_dealloc(tmem, 512);
+    if (warp == TC_EPI_WARPS) {
+        if constexpr (CG2) tmem_dealloc2(tmem, 512);
+        else tmem_dealloc(tmem, 512);
+    }
 }
 
 struct TcPlan {
-    int kb, kp, k_chunks, a_stages, v_stages, nb, la, nwg, wide, splits, tiles_per_split, pair, kv;
+    int kb, kp, k_chunks, a_stages, v_stages, nb, la, nwg, wide, splits, tiles_per_split, pair, kv, cg2;
     int64_t sub_tiles;
     size_t smem_bytes, vimg_bytes, part_bytes;
 };
@@ -1592,7 +1720,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
         sv = sa + la;
     }
     if (sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) return false;
-    if (2 * sa + 2 * sv + 3 * nb + 2 * 3 + 1 > 64) return false;
+    if (3 * sa + 3 * sv + 3 * nb + 2 * 3 + 1 > 64) return false;  // mbarriers (incl. the CG2 relay barriers) fit the array
     pl->kb = kb;
     pl->kp = kp;
     pl->k_chunks = (int)((k + kp - 1) / kp);
@@ -1610,6 +1738,13 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
         const int want = tc_env_int("RLAOPT_B200_TC_PAIR", -1);
         pl->pair = row_blocks >= 2 && (want < 0 ? row_blocks >= 2 * (int64_t)sm_count : want != 0);
         if (kv) pl->pair = 0;
+        // k > 64 (128-column chunks): CTA pairs with cta_group::2 MMAs -- each SM receives half of every operand image.
+        // Correct (same results to the last bit of the error budget) but measured 20 % SLOWER than single-CTA MMAs
+        // (profiles/r02_tc_cg2_ab.log: k = 1000 131.7 -> 104.9 Gentries/s): this family is bound by its epilogue
+        // (pointwise stage + two 64-column drains per tile and warpgroup, profiles/r02_tc_k1000_section_cycles.log), not
+        // by the SM ingress, and coupling two SMs adds their barrier latencies.  Off unless RLAOPT_B200_TC_CG2=1.
+        pl->cg2 = (kp == 128 && !wide && row_blocks >= 2 && tc_env_int("RLAOPT_B200_TC_CG2", 0)) ? 1 : 0;
+        if (pl->cg2) pl->pair = 1;
     }
     pl->kv = kv;
     pl->smem_bytes = sa * a_stage + sv * v_stage + fixed;
@@ -1642,7 +1777,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     splits = (pl->sub_tiles + tps - 1) / tps;
     pl->splits = (int)splits;
     pl->tiles_per_split = (int)tps;
-    pl->vimg_bytes = kv ? (size_t)pl->sub_tiles * (kv + 1) * 256 : (size_t)pl->k_chunks * pl->sub_tiles * ((size_t)kp * 256 + 16);
+    pl->vimg_bytes = kv ? (size_t)pl->sub_tiles * (kv + 1) * 256 : (size_t)pl->k_chunks * pl->sub_tiles * tc_v_record_bytes(kp);
     pl->part_bytes = splits > 1 ? (size_t)splits * n * k * sizeof(float) : 0;
     return true;
 }
@@ -1689,9 +1824,9 @@ size_t tc_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int sm_cou
     return round_up((int64_t)pl.vimg_bytes, 256) + part;
 }
 
-template <int KP, int NWG, bool M12, bool WIDE, int KV = 0, int KIDT = -1>
+template <int KP, int NWG, bool M12, bool WIDE, int KV = 0, int KIDT = -1, bool CG2 = false>
 static cudaError_t launch_tc_inst(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
-    auto kern = kmm_tc_kernel<KP, NWG, M12, WIDE, KV, KIDT>;
+    auto kern = kmm_tc_kernel<KP, NWG, M12, WIDE, KV, KIDT, CG2>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (err != cudaSuccess) return err;
     unsigned row_blocks = (unsigned)((n + TC_BM - 1) / TC_BM);
@@ -1720,6 +1855,16 @@ static cudaError_t launch_tc_kp(const TcParams& p, const TcPlan& pl, int64_t n, 
                 case KID_MATERN32: return launch_tc_inst<KP, NWG, false, true, 0, KID_MATERN32>(p, pl, n, stream);
                 case KID_MATERN52: return launch_tc_inst<KP, NWG, false, true, 0, KID_MATERN52>(p, pl, n, stream);
                 default: return launch_tc_inst<KP, NWG, true, true, 0, KID_MATERN12>(p, pl, n, stream);
+            }
+        }
+    }
+    if constexpr (KP == 128) {
+        if (pl.cg2) {  // CTA pairs with cta_group::2 MMAs
+            switch (p.kid) {
+                case KID_RBF: return launch_tc_inst<KP, NWG, false, false, 0, KID_RBF, true>(p, pl, n, stream);
+                case KID_MATERN32: return launch_tc_inst<KP, NWG, false, false, 0, KID_MATERN32, true>(p, pl, n, stream);
+                case KID_MATERN52: return launch_tc_inst<KP, NWG, false, false, 0, KID_MATERN52, true>(p, pl, n, stream);
+                default: return launch_tc_inst<KP, NWG, true, false, 0, KID_MATERN12, true>(p, pl, n, stream);
             }
         }
     }
@@ -1779,7 +1924,8 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     } else {
         const size_t pack_smem = (size_t)TC_BN * (pl.kp + 1) * sizeof(float);
         dim3 grid((unsigned)pl.sub_tiles, (unsigned)pl.k_chunks);
-        tc_pack_v_kernel<<<grid, 256, pack_smem, stream>>>(V, m, k, ldv, vimg, pl.kp, pl.sub_tiles);
+        const float* col_norms = reinterpret_cast<const float*>(static_cast<const unsigned char*>(cols_packed) + tc_norm_offset());
+        tc_pack_v_kernel<<<grid, 256, pack_smem, stream>>>(V, m, k, ldv, col_norms, vimg, pl.kp, pl.sub_tiles);
         cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) return err;
     }

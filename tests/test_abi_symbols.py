@@ -107,7 +107,7 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
 
 def test_register_contraction_workspace_plan(lib, monkeypatch):
     """k <= 4 on the tensor-core layout: the V workspace is one {V tile, column norms} record of (kv + 1) x 256 B per
-    64-column sub-tile (kv = 1, 2, 4) instead of the fp16 hi/lo image of 16 x 256 + 16 B; RLAOPT_B200_TC_KV=0 switches
+    64-column sub-tile (kv = 1, 2, 4) instead of the fp16 hi/lo record of 16 x 256 + 16 + 256 B; RLAOPT_B200_TC_KV=0 switches
     back.  Host-only: the plan does not touch the GPU."""
     from rlaopt_b200._lib import LAYOUT_TC
 
@@ -116,7 +116,7 @@ def test_register_contraction_workspace_plan(lib, monkeypatch):
     monkeypatch.delenv("RLAOPT_B200_TC_KV", raising=False)
     for k, kv in ((1, 1), (2, 2), (3, 4), (4, 4)):
         assert lib.rlaopt_b200_matmat_workspace_bytes(n, m, d, k, 4, LAYOUT_TC) == sub_tiles * (kv + 1) * 256
-    image = -(-sub_tiles * (16 * 256 + 16) // 256) * 256
+    image = -(-sub_tiles * (16 * 256 + 16 + 64 * 4) // 256) * 256  # fp16 hi | lo image, 1 / s trailer, 64 column norms
     assert lib.rlaopt_b200_matmat_workspace_bytes(n, m, d, 5, 4, LAYOUT_TC) == image
     monkeypatch.setenv("RLAOPT_B200_TC_KV", "0")
     assert lib.rlaopt_b200_matmat_workspace_bytes(n, m, d, 1, 4, LAYOUT_TC) == image
