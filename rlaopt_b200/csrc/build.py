@@ -97,6 +97,41 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+# ---- torch.library front (torch.ops.rlaopt.kernel_matmat): host C++ only, links the C-ABI library ----------------
+TORCH_OP_SRC = "torch_op.cpp"
+TORCH_OP_OUT = os.path.join(HERE, "librlaopt_b200_torch.so")
+TORCH_OP_STAMP = os.path.join(HERE, ".build_stamp_torch")
+
+
+def build_torch_op(force: bool = False) -> str:
+    """g++ torch_op.cpp -> librlaopt_b200_torch.so (registers TORCH_LIBRARY_FRAGMENT(rlaopt, ...); needs the C-ABI
+    library built first).  Rebuilt when the source, the header or the torch version changes."""
+    import torch
+    from torch.utils import cpp_extension
+
+    build(force=False)
+    digest = _file_digest([TORCH_OP_SRC, HEADERS[-1]], torch.__version__)
+    if not force and os.path.exists(TORCH_OP_OUT) and os.path.exists(TORCH_OP_STAMP):
+        with open(TORCH_OP_STAMP) as f:
+            if f.read().strip() == digest:
+                return TORCH_OP_OUT
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else os.environ.get("CXX", "g++")
+    tlib = cpp_extension.library_paths()[0]
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+    cmd += [f"-I{p}" for p in cpp_extension.include_paths()] + ["-I/usr/local/cuda/include"]
+    cmd += [TORCH_OP_SRC, "-o", TORCH_OP_OUT, f"-L{HERE}", "-lrlaopt_b200", f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-lc10",
+            "-ltorch_cuda", "-lc10_cuda", "-Wl,-rpath,$ORIGIN"]
+    proc = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError(f"g++ failed ({proc.returncode}): {' '.join(cmd)}")
+    with open(TORCH_OP_STAMP, "w") as f:
+        f.write(digest)
+    return TORCH_OP_OUT
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(path)
+    print(build_torch_op(force="--force" in sys.argv))

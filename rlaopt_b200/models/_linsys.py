@@ -69,6 +69,9 @@ class Model:
                 if termination_fn(entry["metrics"]["internal_metrics"]):
                     break
         logger._terminate()
+        close = getattr(solver, "close", None)
+        if close is not None:
+            close()  # e.g. the block-prefetch thread of SAP
         return solver.W, log
 
 

@@ -444,8 +444,29 @@ def kernel_matmat(
 
 
 # ---------------------------------------------------------------------------
-# torch.library registration (same pattern as the reference's csc_matmat op).
+# torch.library registration.
+#
+# * ``torch.ops.rlaopt.kernel_matmat`` -- C++ (``csrc/torch_op.cpp``: TORCH_LIBRARY_FRAGMENT(rlaopt, m) + CUDA / CPU
+#   implementations in ``librlaopt_b200_torch.so``), the registration pattern of the reference's own ops
+#   (``rlaopt/csrc/cpp/csc_matmat.cpp:83-87``); loaded by :func:`load_torch_op`.
+# * ``torch.ops.rlaopt_b200.kernel_matmat`` -- the same schema registered from Python over this module's functions
+#   (kept for callers of round 1).
 # ---------------------------------------------------------------------------
+TORCH_OP_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "librlaopt_b200_torch.so")
+_torch_op_loaded = False
+
+
+def load_torch_op() -> bool:
+    """Load ``librlaopt_b200_torch.so`` (once); afterwards ``torch.ops.rlaopt.kernel_matmat`` exists.  Returns False
+    when the library has not been built (``python -m rlaopt_b200.csrc.build``)."""
+    global _torch_op_loaded
+    if not _torch_op_loaded and os.path.exists(TORCH_OP_PATH):
+        _lib.load()  # the op library links the C-ABI library
+        torch.ops.load_library(TORCH_OP_PATH)
+        _torch_op_loaded = True
+    return _torch_op_loaded
+
+
 _TORCH_LIB = torch.library.Library("rlaopt_b200", "FRAGMENT")
 _TORCH_LIB.define(
     "kernel_matmat(Tensor A1, Tensor A2, Tensor V, int kernel_id, float lengthscale, Tensor? lengthscale_vec, "

@@ -13,8 +13,10 @@ block updates are scattered with ``index_add_`` instead of through dense zero ma
 
 Block sampling.  ``torch.multinomial`` over n uniform probabilities on the CPU costs O(n) per step
 (20 ms at n = 1M, 0.2 s at n = 10M -- more than the GPU work of the step).  Two measures:
-the next block is drawn by a helper thread while the GPU works on the current step (same CPU random
-stream, same blocks as the reference; disabled under ``host_rng`` where sketches share that stream),
+the next block is drawn by a helper thread while the GPU works on the current step (from a private generator
+forked off the global CPU stream when the solve starts, so callbacks and user code that draw random numbers never
+interleave with it; under ``host_rng`` -- the parity setting -- the prefetch is off and the blocks come from the global
+stream in the reference's order),
 and ``SAP.block_sampler = "device"`` (or ``RLAOPT_B200_SAP_SAMPLER=device``) draws the block with
 ``torch.multinomial`` on the GPU instead (different stream than the reference, no host work at all).
 """
@@ -62,6 +64,12 @@ class SAP(Solver):
         self._probs_dev = None
         self._pool = None
         self._next_blk = None
+        # Block draws on the helper thread use a PRIVATE generator forked from the global CPU stream at construction:
+        # the global stream is then untouched by the prefetch (callbacks and user code that draw random numbers do not
+        # interleave with it, and no extra block is consumed from it after the last step).  Without prefetch the
+        # blocks come from the global stream itself, in the reference's order (solver parity runs under host_rng).
+        self._gen = None
+        self._np_rng = None
         if accel:
             mu, nu = accel_config.mu, accel_config.nu
             self.beta = 1 - (mu / nu) ** 0.5
@@ -77,11 +85,12 @@ class SAP(Solver):
     # ---- pieces of one step ----
     def _draw_host_blk(self) -> torch.Tensor:
         try:
-            return torch.multinomial(self.probs, self.blk_sz, replacement=False)
+            return torch.multinomial(self.probs, self.blk_sz, replacement=False, generator=self._gen)
         except RuntimeError as err:  # more than 2^24 categories
             if "number of categories cannot exceed" not in str(err):
                 raise
-            pick = np.random.choice(self.probs.shape[0], size=self.blk_sz, replace=False, p=self.probs_cpu)
+            rng = np.random if self._gen is None else self._np_rng
+            pick = rng.choice(self.probs.shape[0], size=self.blk_sz, replace=False, p=self.probs_cpu)
             return torch.from_numpy(pick)
 
     def _get_blk(self) -> torch.Tensor:
@@ -96,12 +105,27 @@ class SAP(Solver):
         prefetch = self.prefetch_blocks and torch.device(self.device).type == "cuda" and not host_rng_enabled()
         if not prefetch:
             blk = self._draw_host_blk()
-        else:  # the CPU stream is only consumed by these draws: drawing one step ahead keeps the sequence
+        else:  # drawing one step ahead on a helper thread, from the solver's private stream
             if self._pool is None:
-                self._pool = ThreadPoolExecutor(max_workers=1)
+                self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="sap-blocks")
+                seed = int(torch.randint(0, 2**62, (1,)).item())  # one draw from the global stream seeds the fork
+                self._gen = torch.Generator().manual_seed(seed)
+                self._np_rng = np.random.default_rng(seed)
             blk = self._next_blk.result() if self._next_blk is not None else self._draw_host_blk()
             self._next_blk = self._pool.submit(self._draw_host_blk)
         return sync_from_rank0(blk, self.device)  # SPMD runs: every rank works on rank 0's block
+
+    def close(self) -> None:
+        """Stop the block-prefetch thread (idempotent; also runs when the solver is collected)."""
+        pool, self._pool, self._next_blk = self._pool, None, None
+        if pool is not None:
+            pool.shutdown(wait=False, cancel_futures=True)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _get_precond(self, blk: torch.Tensor, A_bb=None) -> Preconditioner:
         P = _get_precond(self.precond_config)

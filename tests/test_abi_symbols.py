@@ -123,3 +123,24 @@ def test_register_contraction_workspace_plan(lib, monkeypatch):
     # wide d (X streamed through smem) keeps the MMA2 path
     monkeypatch.delenv("RLAOPT_B200_TC_KV", raising=False)
     assert lib.rlaopt_b200_matmat_workspace_bytes(n, m, 500, 1, 4, LAYOUT_TC) >= image  # + split-column partials
+
+
+def test_torch_library_op_is_registered_from_cpp(lib):
+    """``torch.ops.rlaopt.kernel_matmat``: schema defined by TORCH_LIBRARY_FRAGMENT(rlaopt, m) in csrc/torch_op.cpp (the
+    reference's registration pattern, rlaopt/csrc/cpp/csc_matmat.cpp:83-87); the CPU key raises -- no CPU fallback."""
+    import torch
+
+    from rlaopt_b200 import ops
+    from rlaopt_b200.csrc import build
+
+    build.build_torch_op()
+    assert ops.load_torch_op()
+    schema = str(torch.ops.rlaopt.kernel_matmat.default._schema)
+    assert schema.startswith("rlaopt::kernel_matmat(Tensor A1, Tensor A2, Tensor V, int kernel_id, float lengthscale, "
+                             "Tensor? lengthscale_vec, float const_scaling, bool transpose=False, Tensor? row_idx=None, "
+                             "Tensor? col_idx=None) -> Tensor")
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        torch.ops.rlaopt.kernel_matmat(torch.randn(4, 3), torch.randn(5, 3), torch.randn(5, 2), 0, 1.0, None, 1.0)
+    # the Python-registered twin of round 1 raises the same way
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        torch.ops.rlaopt_b200.kernel_matmat(torch.randn(4, 3), torch.randn(5, 3), torch.randn(5, 2), 0, 1.0, None, 1.0)

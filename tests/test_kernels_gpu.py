@@ -324,3 +324,42 @@ def test_c_abi_one_shot_and_host_entry(dev):
     )
     assert rc == 0, lib.rlaopt_b200_last_error()
     assert ko.rel_fro_error(Yh, ko.kernel_matmat(A1, A2, V, "laplace", 1.0, dtype=torch.float64)) <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_cpp_torch_library_op(dtype):
+    """``torch.ops.rlaopt.kernel_matmat`` (C++ registration, csrc/torch_op.cpp) against the fp64 oracle: all kernels,
+    forward / transpose, gathers, vector operand, per-feature lengthscale, the accuracy-guard fallback, error checks."""
+    from rlaopt_b200 import ops
+
+    assert ops.load_torch_op()
+    op = torch.ops.rlaopt.kernel_matmat
+    dev = torch.device("cuda:0")
+    tol = 1e-5 if dtype == torch.float32 else 1e-11
+    g = torch.Generator().manual_seed(0)
+    n, m, d, k = 700, 1100, 20, 6
+    A1 = (torch.randn(n, d, generator=g, dtype=torch.float64) / d**0.5 + 2.0).to(dtype)  # uncentred on purpose
+    A2 = (torch.randn(m, d, generator=g, dtype=torch.float64) / d**0.5 + 2.0).to(dtype)
+    V, W = torch.randn(m, k, generator=g, dtype=torch.float64).to(dtype), torch.randn(n, k, generator=g, dtype=torch.float64).to(dtype)
+    A1g, A2g, Vg, Wg = A1.to(dev), A2.to(dev), V.to(dev), W.to(dev)
+    for name, kid in ops.KERNEL_IDS.items():
+        ref = ko.kernel_matmat(A1, A2, V, name, 1.3, 0.7, dtype=torch.float64)
+        assert ko.rel_fro_error(op(A1g, A2g, Vg, kid, 1.3, None, 0.7), ref) <= tol, name
+        ref_t = ko.kernel_matmat(A1, A2, W, name, 1.3, 0.7, transpose=True, dtype=torch.float64)
+        assert ko.rel_fro_error(op(A1g, A2g, Wg, kid, 1.3, None, 0.7, True), ref_t) <= tol, name
+    ls = torch.linspace(0.6, 1.8, d, dtype=dtype)
+    rows, cols = torch.randperm(n, generator=g)[:300], torch.randperm(m, generator=g)[:500]
+    ref = ko.kernel_matmat(A1, A2, V[cols, 0:1], "matern52", ls, row_idx=rows, col_idx=cols, dtype=torch.float64)[:, 0]
+    got = op(A1g, A2g, Vg[cols.to(dev), 0].contiguous(), 4, 1.0, ls.to(dev), 1.0, False, rows.to(dev), cols)  # host index list too
+    assert got.shape == (300,) and ko.rel_fro_error(got, ref) <= tol
+    # centred norms beyond the tensor-core budget: the op falls back to direct differences by itself
+    big = (torch.randn(500, 64, generator=g, dtype=torch.float64)).to(dtype)
+    Vb = torch.randn(500, 3, generator=g, dtype=torch.float64).to(dtype)
+    ref = ko.kernel_matmat(big, big, Vb, "rbf", 1.0, dtype=torch.float64)
+    assert ko.rel_fro_error(op(big.to(dev), big.to(dev), Vb.to(dev), 0, 1.0, None, 1.0), ref) <= tol
+    with pytest.raises(RuntimeError, match="same number of features"):
+        op(A1g, A2g[:, :5].contiguous(), Vg, 0, 1.0, None, 1.0)
+    with pytest.raises(RuntimeError, match="dimension mismatch"):
+        op(A1g, A2g, Wg, 0, 1.0, None, 1.0)
+    with pytest.raises(RuntimeError, match="unknown kernel id"):
+        op(A1g, A2g, Vg, 9, 1.0, None, 1.0)
