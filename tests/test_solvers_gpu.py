@@ -119,8 +119,9 @@ def test_krr_pcg_config1_shape():
 
 
 def test_askotch_device_sampler_and_prefetch(monkeypatch):
-    """ASkotch with (a) host blocks prefetched by the helper thread -- the same block sequence as drawing them
-    synchronously -- and (b) blocks sampled on the GPU: unique indices, and the residual goes down."""
+    """ASkotch with (a) host blocks prefetched by the helper thread from the solver's private generator (reproducible,
+    valid blocks; the global CPU stream is left to the caller) and (b) blocks sampled on the GPU: unique indices, and
+    the residual goes down."""
     from rlaopt_b200.solvers import SAP
 
     dev = torch.device("cuda:0")
@@ -147,9 +148,13 @@ def test_askotch_device_sampler_and_prefetch(monkeypatch):
         rel = [float(log[i]["metrics"]["internal_metrics"]["rel_res"].max()) for i in sorted(log)]
         return torch.stack(blocks), rel
 
-    sync_blocks, _ = run("host", False)      # synchronous draws, as the reference does
-    pre_blocks, rel_pre = run("host", True)  # prefetched draws: same CPU stream, same sequence
-    assert torch.equal(sync_blocks, pre_blocks[: len(sync_blocks)])
+    sync_blocks, _ = run("host", False)      # synchronous draws from the global CPU stream, as the reference does
+    pre_blocks, rel_pre = run("host", True)  # prefetched draws: private generator forked off the global stream
+    pre_again, _ = run("host", True)
+    assert torch.equal(pre_blocks, pre_again)  # reproducible for a fixed seed
+    assert pre_blocks.shape == sync_blocks.shape and not torch.equal(pre_blocks, sync_blocks)
+    assert all(len(torch.unique(b)) == len(b) for b in pre_blocks)
+    assert int(pre_blocks.min()) >= 0 and int(pre_blocks.max()) < case["n"]
     dev_blocks, rel_dev = run("device", True)
     assert all(len(torch.unique(b)) == len(b) for b in dev_blocks)
     assert int(dev_blocks.min()) >= 0 and int(dev_blocks.max()) < case["n"]
