@@ -13,4 +13,4 @@ fi
 $TR --master-port 29521 bench.py --gpus $N --steps 2 --warmup 1 --workload c3_laplace --no-krr > gpurun_out/r02_bench_c3_laplace_n$N.json 2> gpurun_out/r02_bench_c3_laplace_n$N.err; echo "laplace rc=$?"
 $TR --master-port 29522 bench.py --gpus $N --steps 3 --warmup 2 --workload c3_matern52 --no-krr > gpurun_out/r02_bench_c3_matern52_n$N.json 2> gpurun_out/r02_bench_c3_matern52_n$N.err; echo "matern rc=$?"
 for f in gpurun_out/r02_bench_*_n$N.json; do echo "== $f"; tail -c 1500 $f; echo; done
-tail -3 gpurun_out/r02_bench_*_n$N.err
+for f in gpurun_out/r02_bench_*_n$N.err; do tail -n 2 $f; done
