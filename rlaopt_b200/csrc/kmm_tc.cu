@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     if (warp >= TC_EPI_WARPS) {
     // registers move from this warpgroup (producer, MMA issue, two idle warps) to the epilogue warpgroups
     if constexpr (NWG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // NWG = 3: 152 for the epilogue, NWG = 4: 104
     if (warp == TC_EPI_WARPS) {
         // =============================== producer ===============================
         if (lane == 0) {
@@ -897,7 +897,10 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         // O[ob] = P[b] . V_tile : fresh accumulator per sub-tile, fp16 pairs, K = 16 per instruction
         auto issue_mma2 = [&](int b, int ob, int s) {
             const uint32_t d_t = tmem + col_o + ob * KP;
-            const uint32_t p_hi = tmem + col_sp + b * 64, p_lo = p_hi + 32;
+            // P' layout in the S/P buffer: hi pairs in columns [0, 32), lo pairs in [32, 64); the quarter-row epilogue
+            // (NWG = 4) interleaves them per 16 entries: hi of K-step ks at 16 ks, lo at 16 ks + 8
+            constexpr uint32_t p_step = NWG == 4 ? 16 : 8;
+            const uint32_t p_hi = tmem + col_sp + b * 64, p_lo = p_hi + (NWG == 4 ? 8 : 32);
             const uint32_t img = v_ring_base + (uint32_t)s * v_stage_bytes;
             const uint32_t dlo_hi = desc_lo0 + (img >> 4);
             const uint32_t dlo_lo = desc_lo0 + ((img + v_lo_off) >> 4);
@@ -908,7 +911,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                     const uint32_t bd = (part == 0 ? dlo_lo : dlo_hi);
 #pragma unroll
                     for (int ks = 0; ks < TC_BN / 16; ++ks) {
-                        mma_ts(d_t, a + ks * 8, bd + ks * 2, desc_hi, idesc2, (part | ks) != 0);
+                        mma_ts(d_t, a + ks * p_step, bd + ks * 2, desc_hi, idesc2, (part | ks) != 0);
                     }
                 }
             }
@@ -1083,7 +1086,8 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     }
     } else {
         if constexpr (NWG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        else if constexpr (NWG == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // =============================== epilogue warps ===============================
         const int q = warp & 3;   // TMEM lane quarter this warp may access
         const int h = warp >> 2;  // column half of the sub-tile / of O handled by this warp
@@ -1130,6 +1134,8 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         // so a thread still carries 64 accumulators; the owner publishes the tile's scale through smem.
         constexpr bool SPLIT = KP > 64;
         constexpr bool FRAG = KV > 0 && !M12;
+        constexpr bool QUART = NWG == 4;  // quarter-row epilogue of the four-warpgroup instantiations (KP <= 32, not Matern-1/2)
+        static_assert(!QUART || (KV == 0 && !SPLIT && !M12 && !WIDE), "four epilogue warpgroups: small-d/k families only");
         constexpr int DW = SPLIT ? KP / 2 : KP;  // O columns one thread accumulates
         uint64_t acc[DW / 2];                    // fp32 pairs
 #pragma unroll
@@ -1212,6 +1218,96 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             TC_PROF(1)
             tc_fence_after();
             const uint32_t t_s = tmem + lane_bits + col_sp + b * 64;
+            if constexpr (QUART) {
+                // ---- four epilogue warpgroups, 104 registers per thread: the row is never held whole.  Pass 1 reads S in
+                // two halves for the row extreme; pass 2 re-reads it in quarters (the load of quarter q + 1 is in flight
+                // while quarter q runs through the special-function pipe), recomputes z and writes P' in place:
+                // quarter q (S columns 16 q .. 16 q + 15) becomes P'_hi in columns 16 q .. 16 q + 7 and P'_lo in columns
+                // 16 q + 8 .. 16 q + 15 -- nothing unread is overwritten (issue_mma2 addresses A with that stride) ----
+                const float vinv = *reinterpret_cast<const float*>(vst + KP * 256);
+                const float4* nyq = reinterpret_cast<const float4*>(vst + v_norm_off);
+                float ext = is_rbf ? -3.0e38f : 3.0e38f;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t sh[32];
+                    tmem_ld32(t_s + hh * 32, sh);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 ny4 = nyq[hh * 8 + i];
+                        float z0, z1, z2, z3;
+                        unpack2(fma2(pack2(__uint_as_float(sh[4 * i]), __uint_as_float(sh[4 * i + 1])), za2,
+                                     fma2(pack2(ny4.x, ny4.y), zc2, zx2)), z0, z1);
+                        unpack2(fma2(pack2(__uint_as_float(sh[4 * i + 2]), __uint_as_float(sh[4 * i + 3])), za2,
+                                     fma2(pack2(ny4.z, ny4.w), zc2, zx2)), z2, z3);
+                        if (is_rbf) ext = fmaxf(max3(ext, z0, z1), fmaxf(z2, z3));
+                        else ext = fminf(min3(ext, z0, z1), fminf(z2, z3));
+                    }
+                }
+                int E;
+                if (is_rbf) {
+                    E = 14 - __float2int_rd(fmaxf(ext, -200.0f));
+                } else {
+                    float pmax;
+                    if (kid == KID_MATERN32) pmax = tc_value<KID_MATERN32>(ext);
+                    else pmax = tc_value<KID_MATERN52>(ext);
+                    E = 14 + 127 - (int)((__float_as_uint(pmax) >> 23) & 0xFF);
+                }
+                E = max(0, min(E, 120));
+                const float Ef = (float)E;
+                const float dsc = __uint_as_float((uint32_t)(127 - E) << 23) * vinv;
+                const uint64_t E2 = pack2(Ef, Ef);
+                const uint64_t nl2 = pack2(-TC_LOG2E, -TC_LOG2E), one2 = pack2(1.0f, 1.0f),
+                               third2 = pack2(1.0f / 3.0f, 1.0f / 3.0f);
+                uint32_t sq[2][16];
+                tmem_ld16(t_s, sq[0]);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    tmem_wait_ld();  // quarter q4 is in registers
+                    if (q4 < 3) tmem_ld16(t_s + (q4 + 1) * 16, sq[(q4 + 1) & 1]);
+                    uint32_t pq[16];  // [0, 8): P'_hi pairs, [8, 16): P'_lo pairs
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 ny4 = nyq[q4 * 4 + i];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const uint64_t zz = fma2(pack2(__uint_as_float(sq[q4 & 1][4 * i + 2 * e]), __uint_as_float(sq[q4 & 1][4 * i + 2 * e + 1])),
+                                                     za2, fma2(e == 0 ? pack2(ny4.x, ny4.y) : pack2(ny4.z, ny4.w), zc2, zx2));
+                            float p0, p1;
+                            if (is_rbf) {
+                                float a0, a1;
+                                unpack2(add2(zz, E2), a0, a1);
+                                p0 = ex2_approx(a0);
+                                p1 = ex2_approx(a1);
+                            } else {
+                                float z0, z1;
+                                unpack2(zz, z0, z1);
+                                const uint64_t r2 = pack2(sqrt_approx(fmaxf(z0, 0.0f)), sqrt_approx(fmaxf(z1, 0.0f)));
+                                float a0, a1;
+                                unpack2(fma2(r2, nl2, E2), a0, a1);
+                                uint64_t pp = pack2(ex2_approx(a0), ex2_approx(a1));
+                                if (kid == KID_MATERN32) pp = mul2(pp, add2(r2, one2));
+                                else pp = mul2(pp, fma2(r2, fma2(r2, third2, one2), one2));
+                                unpack2(pp, p0, p1);
+                            }
+                            const __half2 h2 = __floats2half2_rn(p0, p1);
+                            const float2 f2 = __half22float2(h2);
+                            float l0, l1;
+                            unpack2(sub2(pack2(p0, p1), pack2(f2.x, f2.y)), l0, l1);
+                            const __half2 l2 = __floats2half2_rn(l0, l1);
+                            pq[2 * i + e] = *reinterpret_cast<const uint32_t*>(&h2);
+                            pq[8 + 2 * i + e] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                    }
+                    tmem_st16(t_s + q4 * 16, pq);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive_pair(&p_full[b]);
+                if (u >= NWG) drain(g, (uint32_t)(((u - NWG) / NWG) & 1), dsc_prev);
+                dsc_prev = dsc;
+            } else {
             uint32_t s0[32], s1[32];
             if constexpr (FRAG) {
                 tmem_ld_16x256b_x8(t_s, s0);                // lanes 32q + [0, 16)
@@ -1545,6 +1641,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             dsc_prev = dsc;
             }
             }
+            }  // !QUART
             b += NWG;
             if (b >= NB) {
                 b -= NB;
@@ -1677,7 +1774,8 @@ int tc_env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* pl) {
+// kid: kernel id when known (the launch), -1 for sizing queries -- the workspace does not depend on what it selects
+bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* pl, int kid = -1) {
     if (d < 1 || d > TC_MAX_D_WIDE || n < 1 || m < 1 || k < 1) return false;
     const bool wide = d > TC_MAX_D;
     const int kb = tc_kblocks(d);
@@ -1688,7 +1786,14 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     if (k > 64 && (wide ? 0 : 64 * kb) + (wide ? 4 : 2) * 64 + 2 * 128 <= 512 && tc_env_int("RLAOPT_B200_TC_KP128", 1)) kp = 128;
     // Small d and k: the tensor work per tile is small and the kernel is bound by the pointwise stage (MUFU, TMEM
     // and mbarrier latencies); a third epilogue warpgroup keeps three tiles in flight per SM sub-partition.
-    int nwg = (kb <= 2 && kp <= 32 && tc_env_int("RLAOPT_B200_TC_NWG", 3) == 3) ? 3 : 2;
+    const int nwg_env = tc_env_int("RLAOPT_B200_TC_NWG", 3);
+    int nwg = (kb <= 2 && kp <= 32 && nwg_env >= 3) ? 3 : 2;
+    // A fourth one (quarter-row epilogue, 104 registers per thread; k <= 16, every kernel but Matern-1/2, whose near-pair
+    // recompute holds the whole row) was built to fill the special-function pipe (XU 75 % busy with three warps per
+    // sub-partition, profiles/r02_ncu_tc_matern52_c3_summary.md).  Correct, but its extra TMEM round trips cost more than
+    // the fourth warp brings: Matern-5/2 d=32 k=16 1603 -> 1576, RBF 2475 -> 2185 Gentries/s (profiles/r02_tc_nwg4_ab.log).
+    // Only with RLAOPT_B200_TC_NWG=4.
+    if (nwg == 3 && kp == 16 && nwg_env >= 4 && kid >= 0 && kid != KID_MATERN12 && k > 4) nwg = 4;
     // k <= 4 (single right-hand sides: PCG, SAP / ASkotch oracles): the contraction with V runs on the CUDA cores in
     // the epilogue -- one FFMA2 per two entries and column instead of the fp16 split of P, its TMEM store, MMA2 and
     // the accumulator drain.  Three epilogue warpgroups, no CTA pairs.  RLAOPT_B200_TC_KV=0 switches it off.
@@ -1720,7 +1825,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
         sv = sa + la;
     }
     if (sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) return false;
-    if (3 * sa + 3 * sv + 3 * nb + 2 * 3 + 1 > 64) return false;  // mbarriers (incl. the CG2 relay barriers) fit the array
+    if (3 * sa + 3 * sv + 3 * nb + 2 * nwg + 1 > 64) return false;  // mbarriers (incl. the CG2 relay barriers) fit the array
     pl->kb = kb;
     pl->kp = kp;
     pl->k_chunks = (int)((k + kp - 1) / kp);
@@ -1880,6 +1985,15 @@ static cudaError_t launch_tc_kp(const TcParams& p, const TcPlan& pl, int64_t n, 
     }
 }
 
+// four epilogue warpgroups (quarter-row epilogue): k <= 16, RBF / Matern-3/2 / Matern-5/2
+static cudaError_t launch_tc_nwg4(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
+    switch (p.kid) {
+        case KID_RBF: return launch_tc_inst<16, 4, false, false, 0, KID_RBF>(p, pl, n, stream);
+        case KID_MATERN32: return launch_tc_inst<16, 4, false, false, 0, KID_MATERN32>(p, pl, n, stream);
+        default: return launch_tc_inst<16, 4, false, false, 0, KID_MATERN52>(p, pl, n, stream);
+    }
+}
+
 // register-contraction instantiations: (k <= 1, 2, 4) x (RBF, Matern-3/2, Matern-5/2 fixed at compile time; Matern-1/2
 // with its near-pair recompute), three epilogue warpgroups
 template <int KV, int KIDT>
@@ -1908,7 +2022,7 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
                       int sm_count, void* workspace, size_t workspace_bytes, cudaStream_t stream, bool keep_partials,
                       int* splits_out, const float** part_out) {
     TcPlan pl;
-    if (!tc_plan(n, m, d, k, sm_count, &pl)) return cudaErrorInvalidValue;
+    if (!tc_plan(n, m, d, k, sm_count, &pl, kid)) return cudaErrorInvalidValue;
     const size_t v_bytes = (size_t)round_up((int64_t)pl.vimg_bytes, 256);
     const size_t part_bytes = keep_partials ? (size_t)pl.splits * n * k * sizeof(float) : pl.part_bytes;
     if (workspace == nullptr || workspace_bytes < v_bytes + part_bytes) return cudaErrorInvalidValue;
@@ -1966,7 +2080,11 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
         err = launch_tc_kv(p, pl, n, stream);
     } else
     switch (pl.kp) {
-        case 16: err = pl.nwg == 3 ? launch_tc_kp<16, 3>(p, pl, n, stream) : launch_tc_kp<16, 2>(p, pl, n, stream); break;
+        case 16:
+            err = pl.nwg == 4   ? launch_tc_nwg4(p, pl, n, stream)
+                  : pl.nwg == 3 ? launch_tc_kp<16, 3>(p, pl, n, stream)
+                                : launch_tc_kp<16, 2>(p, pl, n, stream);
+            break;
         case 32: err = pl.nwg == 3 ? launch_tc_kp<32, 3>(p, pl, n, stream) : launch_tc_kp<32, 2>(p, pl, n, stream); break;
         case 64: err = launch_tc_kp<64, 2>(p, pl, n, stream); break;
         default: err = launch_tc_kp<128, 2>(p, pl, n, stream); break;
