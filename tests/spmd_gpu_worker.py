@@ -71,6 +71,47 @@ def main():
         other = T.clone()
         dist.broadcast(other, src=0)
         ok &= bool(torch.equal(T, other))
+    # ---- round 2: row-sharded solver state, fused products on the shards, host delivery ----
+    from rlaopt_b200.linops import apply_fused
+    from rlaopt_b200.solvers._pcg import PCG
+    from rlaopt_b200.solvers._pcg_sharded import ShardedPCG
+    from rlaopt_b200.utils import SharedPinnedTensor
+
+    k16 = 16
+    B16 = torch.randn(n, k16, generator=g)
+    B16[:, :5] = (K @ B16[:, :5].double()).float()  # smooth right-hand sides converge first: partial masks
+    res = {}
+    for sharded in ("1", "0"):
+        for mode in ("true", "recurrence"):
+            os.environ["RLAOPT_B200_SHARDED_STATE"] = sharded
+            system = LinSys(A, B16.to(dev), reg=0.5)
+            torch.manual_seed(200 + rank)
+            with replicated_rng():
+                Ws, logs = system.solve(
+                    PCGConfig(device=dev, max_iters=80, rtol=1e-4, precond_config=NystromConfig(rank=80, rho=0.5, sketch="gauss")),
+                    torch.zeros(n, k16, device=dev), callback_freq=1, residual=mode)
+            ok &= isinstance(system._solver, ShardedPCG if sharded == "1" else PCG)
+            ok &= bool((logs[max(logs)]["metrics"]["internal_metrics"]["rel_res"] <= 1e-4).all())
+            res[(sharded, mode)] = (Ws, max(logs))
+    os.environ.pop("RLAOPT_B200_SHARDED_STATE", None)
+    ref16 = torch.linalg.solve(K + 0.5 * torch.eye(n, dtype=torch.float64), B16.double())
+    for key, (Ws, its) in res.items():
+        ok &= bool(torch.linalg.norm(Ws.cpu().double() - ref16) <= 2e-3 * torch.linalg.norm(ref16))
+        ok &= abs(its - res[("0", "true")][1]) <= 2
+    # fused product on the row shards: terms on every rank's rows, Gram and norms all-reduced
+    C, Lg = torch.randn(n, k, generator=g), torch.randn(n, 2, generator=g)
+    Yf, Gf, Sf = apply_fused(A, V.to(dev), alpha=-1.0, addend=C.to(dev), beta=0.25, rhs=B.to(dev), gamma=1.0,
+                             gram_with=Lg.to(dev), want_sqnorm=True)
+    reff = B.double() - K @ V.double() + 0.25 * C.double()
+    ok &= ko.rel_fro_error(Yf, reff) <= 1e-5 and ko.rel_fro_error(Gf, Lg.double().T @ reff) <= 1e-4
+    ok &= ko.rel_fro_error(Sf, (reff * reff).sum(0)) <= 1e-4
+    # result delivered into host memory mapped by both ranks, each rank its own rows
+    shared = SharedPinnedTensor("spmd_gpu_test", (n, k))
+    shared.tensor.zero_()
+    dist.barrier()
+    A.matmat_to_host(V.to(dev), shared.tensor)
+    ok &= ko.rel_fro_error(shared.tensor, K @ V.double()) <= 1e-5
+    shared.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
