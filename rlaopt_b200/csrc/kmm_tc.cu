@@ -335,77 +335,138 @@ __device__ __forceinline__ int64_t tc_src_row(const int64_t* __restrict__ idx, i
     return (s >= 0 && s < n_src) ? s : -1;
 }
 
-__global__ void tc_absmax_kernel(const float* __restrict__ X, int64_t n, int64_t n_src, int64_t d, int64_t ldx,
-                                 const int64_t* __restrict__ idx, float inv_ls, const float* __restrict__ inv_ls_vec,
-                                 const float* __restrict__ center, TcHeader* hdr) {
+// abs-max of the centred, scaled points: a block owns TC_ABSMAX_ROWS rows; lanes walk the features of 8 rows at a time
+// (128-byte row segments, no index arithmetic per element)
+constexpr int TC_ABSMAX_ROWS = 512;
+__global__ void __launch_bounds__(256)
+tc_absmax_kernel(const float* __restrict__ X, int64_t n, int64_t n_src, int64_t d, int64_t ldx,
+                 const int64_t* __restrict__ idx, float inv_ls, const float* __restrict__ inv_ls_vec,
+                 const float* __restrict__ center, TcHeader* hdr) {
+    const int fx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * TC_ABSMAX_ROWS;
+    const int64_t r1 = min(n, r0 + TC_ABSMAX_ROWS);
     float mx = 0.0f;
-    const int64_t total = n * d;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = e / d, f = e % d;
+    for (int64_t i = r0 + ry; i < r1; i += 8) {
         const int64_t src = tc_src_row(idx, i, n_src);
         if (src < 0) continue;
-        const float s = inv_ls_vec ? inv_ls_vec[f] : inv_ls;
-        const float c = center ? center[f] : 0.0f;
-        const float v = fabsf((X[src * ldx + f] - c) * s);
-        if (v < 3.0e38f) mx = fmaxf(mx, v);  // ignore inf / nan here; they propagate through the values
+        const float* row = X + src * ldx;
+        for (int64_t f = fx; f < d; f += 32) {
+            const float s = inv_ls_vec ? inv_ls_vec[f] : inv_ls;
+            const float c = center ? center[f] : 0.0f;
+            const float v = fabsf((row[f] - c) * s);
+            if (v < 3.0e38f) mx = fmaxf(mx, v);  // ignore inf / nan here; they propagate through the values
+        }
     }
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0 && mx > 0.0f) atomicMax(&hdr->absmax_bits, __float_as_uint(mx));
+    __shared__ float red[8];
+    if (fx == 0) red[ry] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+        if (mx > 0.0f) atomicMax(&hdr->absmax_bits, __float_as_uint(mx));
+    }
 }
 
-// one thread per (padded) point: fp16 hi/lo split into the swizzled tile image + squared norm.
+// One block per 64-point tile image: fp16 hi/lo split into the swizzled image + squared norms.
+//   phase A  the tile's 64 points x 64 features of a K-block go through shared memory (row gather, center, 1/l and the
+//            power-of-two scale applied on the way): global reads are 128-byte row segments;
+//   phase B  thread (row r, physical 16-byte chunk j) converts logical chunk j ^ (r & 7): a warp stores four whole
+//            128-byte image rows (512 contiguous bytes) per instruction, hi then lo.
 // `center` (optional, one value per feature, in the units of X): every kernel here is a function of x - y, so the
 // same vector subtracted from both operands leaves K unchanged while it shrinks |x|^2 + |y|^2 -- and with it the
 // absolute error eps (|x|^2 + |y|^2) of the GEMM-form distance.
-__global__ void tc_pack_points_kernel(const float* __restrict__ X, int64_t n, int64_t n_src, int64_t d, int64_t ldx,
-                                      const int64_t* __restrict__ idx, float inv_ls,
-                                      const float* __restrict__ inv_ls_vec, const float* __restrict__ center,
-                                      unsigned char* __restrict__ packed, int kb_count) {
+__global__ void __launch_bounds__(256)
+tc_pack_points_kernel(const float* __restrict__ X, int64_t n, int64_t n_src, int64_t d, int64_t ldx,
+                      const int64_t* __restrict__ idx, float inv_ls, const float* __restrict__ inv_ls_vec,
+                      const float* __restrict__ center, unsigned char* __restrict__ packed, int kb_count) {
+    __shared__ float tile[TC_BN][TC_BN + 1];
+    __shared__ int64_t srcs[TC_BN];
+    __shared__ float wred[8];
+    __shared__ unsigned int bad_cnt;
     TcHeader* hdr = reinterpret_cast<TcHeader*>(packed);
     const float absmax = __uint_as_float(hdr->absmax_bits);
     float s = 1.0f;
     if (absmax > 0.0f) s = ldexpf(1.0f, 12 - ilogbf(absmax));
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) {
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid == 0) {
         hdr->scale = s;
         hdr->inv_scale = 1.0f / s;
     }
-    const int64_t n_pad = tc_npad(n);
-    if (i >= n_pad) return;
+    const int64_t i0 = (int64_t)blockIdx.x * TC_BN;
+    if (tid == 0) bad_cnt = 0;
+    __syncthreads();
+    if (tid < TC_BN) {
+        const int64_t i = i0 + tid;
+        const int64_t src = (i < n) ? tc_src_row(idx, i, n_src) : -1;
+        srcs[tid] = src;
+        if (i < n && src < 0) atomicAdd(&bad_cnt, 1u);
+    }
+    __syncthreads();
     float* norms = reinterpret_cast<float*>(packed + tc_norm_offset());
-    unsigned char* img = packed + tc_image_offset(n) + (size_t)(i >> 6) * tc_image_bytes(kb_count);
-    const int r = (int)(i & 63);
-    const int64_t src = (i < n) ? tc_src_row(idx, i, n_src) : -1;
-    if (i < n && src < 0) atomicAdd(&hdr->bad_index, 1u);
-    double nrm = 0.0;
+    unsigned char* img = packed + tc_image_offset(n) + (size_t)blockIdx.x * tc_image_bytes(kb_count);
+    const int j = tid & 7;  // physical 16-byte chunk of the image row
+    double nrm[2] = {0.0, 0.0};
     for (int kb = 0; kb < kb_count; ++kb) {
-        for (int c = 0; c < 8; ++c) {
+        {   // phase A: feature fa of rows (tid >> 6) + 4 it
+            const int fa = tid & 63;
+            const int64_t f = (int64_t)kb * 64 + fa;
+            const float sc = (f < d) ? (inv_ls_vec ? inv_ls_vec[f] : inv_ls) : 0.0f;
+            const float cf = (f < d && center) ? center[f] : 0.0f;
+#pragma unroll 4
+            for (int it = 0; it < 16; ++it) {
+                const int r = (tid >> 6) + 4 * it;
+                const int64_t src = srcs[r];
+                float v = 0.0f;
+                if (src >= 0 && f < d) v = (X[src * ldx + f] - cf) * sc * s;
+                tile[r][fa] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {  // phase B
+            const int r = (tid >> 3) + 32 * half;
+            const int c = j ^ (r & 7);  // logical chunk stored at physical position j
             alignas(16) __half hi[8];
             alignas(16) __half lo[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int64_t f = (int64_t)kb * 64 + c * 8 + e;
-                float v = 0.0f;
-                if (src >= 0 && f < d)
-                    v = (X[src * ldx + f] - (center ? center[f] : 0.0f)) * (inv_ls_vec ? inv_ls_vec[f] : inv_ls) * s;
+                const float v = tile[r][c * 8 + e];
                 const __half h = __float2half_rn(v);
                 const __half l = __float2half_rn(v - __half2float(h));
                 hi[e] = h;
                 lo[e] = l;
                 const double eff = (double)__half2float(h) + (double)__half2float(l);
-                nrm += eff * eff;
+                nrm[half] += eff * eff;
             }
-            const size_t off = (size_t)kb * TC_KBLOCK_BYTES + (size_t)r * 128 + (size_t)((c ^ (r & 7)) * 16);
+            const size_t off = (size_t)kb * TC_KBLOCK_BYTES + (size_t)r * 128 + (size_t)(j * 16);
             *reinterpret_cast<uint4*>(img + off) = *reinterpret_cast<const uint4*>(hi);
             *reinterpret_cast<uint4*>(img + (size_t)kb_count * TC_KBLOCK_BYTES + off) = *reinterpret_cast<const uint4*>(lo);
         }
+        __syncthreads();
     }
-    const float nrm_f = (float)(nrm / ((double)s * (double)s));
-    norms[i] = nrm_f;
+    // row norms: the eight lanes of a row hold the partial sums of their chunks (fp64, fixed order)
+    float wmax = 0.0f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        double t = nrm[half];
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+        const float nrm_f = (float)(t / ((double)s * (double)s));
+        if (j == 0) norms[i0 + (tid >> 3) + 32 * half] = nrm_f;
+        if (nrm_f < 3.0e38f) wmax = fmaxf(wmax, nrm_f);
+    }
     // accuracy guard input: the largest squared norm of the set (non-negative floats order like their bit patterns)
-    float wmax = (nrm_f < 3.0e38f) ? nrm_f : 0.0f;
     for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if ((threadIdx.x & 31) == 0 && wmax > 0.0f) atomicMax(&hdr->max_sqnorm_bits, __float_as_uint(wmax));
+    if ((tid & 31) == 0) wred[tid >> 5] = wmax;
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) wmax = fmaxf(wmax, wred[w]);
+        if (wmax > 0.0f) atomicMax(&hdr->max_sqnorm_bits, __float_as_uint(wmax));
+        if (bad_cnt > 0) atomicAdd(&hdr->bad_index, bad_cnt);
+    }
 }
 
 // bytes of one V record in the workspace: fp16 image (hi | lo), 16 B trailer {1 / s}, 64 column norms
@@ -1908,13 +1969,11 @@ cudaError_t launch_tc_pack(const float* X, int64_t n, int64_t n_src, int64_t d, 
                            cudaStream_t stream) {
     cudaError_t err = cudaMemsetAsync(packed, 0, TC_HEADER_BYTES, stream);
     if (err != cudaSuccess) return err;
-    const int64_t total = n * d;
-    int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    if (blocks < 1) blocks = 1;
-    tc_absmax_kernel<<<blocks, 256, 0, stream>>>(X, n, n_src, d, ldx, idx, inv_ls, inv_ls_vec, center,
-                                                 reinterpret_cast<TcHeader*>(packed));
+    const unsigned blocks = (unsigned)((n + TC_ABSMAX_ROWS - 1) / TC_ABSMAX_ROWS);
+    tc_absmax_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(X, n, n_src, d, ldx, idx, inv_ls, inv_ls_vec, center,
+                                                                 reinterpret_cast<TcHeader*>(packed));
     const int64_t n_pad = tc_npad(n);
-    tc_pack_points_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, stream>>>(
+    tc_pack_points_kernel<<<(unsigned)(n_pad / TC_BN), 256, 0, stream>>>(
         X, n, n_src, d, ldx, idx, inv_ls, inv_ls_vec, center, static_cast<unsigned char*>(packed), tc_kblocks(d));
     return cudaGetLastError();
 }
