@@ -105,7 +105,8 @@ class RowShardedLinOp(_BaseLinOp):
             dst = host_out[self.lo:self.hi]
             dst.copy_(loc.reshape(dst.shape), non_blocking=True)
         if wait:
-            torch.cuda.current_stream(self._device).synchronize() if self._device.type == "cuda" else None
+            if self._device.type == "cuda":
+                torch.cuda.current_stream(self._device).synchronize()
             dist.barrier(group=self.group)
         return host_out[:, 0] if (vec and host_out.ndim == 2) else host_out
 
