@@ -341,6 +341,31 @@ SECONDARY = {
 }
 
 
+def sampled_rows_check(kernel: str, A1: torch.Tensor, A2: torch.Tensor, V: torch.Tensor, Y: torch.Tensor, rows: int = 64) -> dict:
+    """Relative Frobenius error of `rows` sampled rows of Y = K(A1, A2) @ V against the reference formulas
+    (rlaopt/kernels/standard.py:46-85) evaluated in fp64 on the device, lengthscale 1 -- every bench number carries its
+    own parity figure at the size it was measured at (the CPU oracle checks the same shapes in tests/)."""
+    n = A1.shape[0]
+    idx = torch.linspace(0, n - 1, rows, device=A1.device).long()
+    Xs, ref = A1[idx].double(), None
+    V2 = V if V.ndim == 2 else V[:, None]
+    for c0 in range(0, A2.shape[0], 500_000):
+        Xc = A2[c0:c0 + 500_000].double()
+        if kernel == "laplace":
+            Kc = torch.exp(-torch.cdist(Xs, Xc, p=1))
+        else:
+            D2 = torch.cdist(Xs, Xc).pow(2)
+            if kernel == "rbf":
+                Kc = torch.exp(-0.5 * D2)
+            else:
+                s5 = (5.0 * D2).sqrt()
+                Kc = (1 + s5 + s5 * s5 / 3) * torch.exp(-s5)
+        part = Kc @ V2[c0:c0 + 500_000].double()
+        ref = part if ref is None else ref + part
+    got = (Y if Y.ndim == 2 else Y[:, None])[idx].double()
+    return {"rows": rows, "rel_err_vs_fp64": float((got - ref).norm() / ref.norm()), "bar": 1e-5}
+
+
 def binding_roofline(kernel: str, d: int, k: int, entries: float, seconds: float, layout_tc: bool, peaks: dict,
                      sm_mhz, sustained: bool = False) -> dict:
     """Roofline of the BINDING pipe ("report the binding one"):
@@ -417,6 +442,7 @@ def secondary_leg(name: str, dev, peaks: dict, gpu_index: int, warm: int = 2, st
         "clocks": clocks,
         "gpu_launches": ops.LAUNCH_COUNT - launches0,
         "checksum_abs_sum": float(Y.double().abs().sum().item()),
+        "parity": sampled_rows_check(kernel, X[:rows], X, V, Y),
     }
     del op, X, V, Y
     torch.cuda.empty_cache()
@@ -621,6 +647,7 @@ def run_ours(args) -> int:
     ms_per_step = total_ms / args.steps
     value = n * n / (ms_per_step * 1e-3) / 1e9
     checksum = float(Y.double().abs().sum().item())
+    parity = sampled_rows_check(kernel, op.A1, op.A2, Vg, Y) if (rank == 0 and kernel in ("rbf", "laplace", "matern52")) else None
 
     # ---- end to end through the public API with host buffers ----------------------------------
     # N = 1: the result is read back into pinned host memory.  N > 1: the caller's result buffer is host memory that
@@ -781,6 +808,7 @@ def run_ours(args) -> int:
         "roofline": roofline,
         "kernel_path": "tcgen05" if layout == _lib.LAYOUT_TC else "cuda-core",
         "checksum_abs_sum": checksum,
+        "parity": parity,
     }
     if world == 1 and not args.no_cpu_baseline:
         base = cpu_baseline(kernel, X, V, budget_s=args.ref_budget_s)

@@ -277,6 +277,49 @@ def test_full_size_c2_sampled_rows(dev):
     assert ko.rel_fro_error(Yt, ref) <= 1e-5
 
 
+@pytest.mark.parametrize(
+    "name,n,d,k,rows",
+    [("laplace", 4_000_000, 32, 16, 2048),       # BASELINE configs[2], CUDA-core kernel
+     ("matern52", 4_000_000, 32, 16, 4096),      # BASELINE configs[2], tcgen05 kernel (pointwise-bound family)
+     ("rbf", 10_000_000, 16, 1, 4096),           # BASELINE configs[3]: the ASkotch row-oracle product (register contraction)
+     ("rbf", 2_000_000, 64, 1000, 1024)],        # BASELINE configs[4]: the Nystrom sketch (k > 64 family, 8 column chunks)
+)
+def test_full_size_baseline_shapes_sampled_rows(dev, name, n, d, k, rows):
+    """The other BASELINE shapes at their FULL column count: a row block ``K(X[blk], X) @ V`` through the row oracle
+    (what ASkotch and a sharded rank compute), checked on 24 of its rows against the fp64 oracle, plus two
+    size-independent properties: linearity in V and invariance under the row partition."""
+    import rlaopt_b200.kernels as kernels
+    from rlaopt_b200.kernels import KernelConfig
+
+    g = torch.Generator().manual_seed(7)
+    X = torch.randn(n, d, generator=g) / d**0.5
+    V = torch.randn(n, k, generator=g)
+    if k == 1000:
+        V /= k**0.5
+    cls = {"laplace": kernels.LaplaceLinOp, "matern52": kernels.Matern52LinOp, "rbf": kernels.RBFLinOp}[name]
+    Xg, Vg = X.to(dev), V.to(dev)
+    op = cls(Xg, Xg, KernelConfig(lengthscale=1.0))
+    blk = torch.randperm(n, generator=g)[:rows]
+    Y = op.row_oracle(blk) @ (Vg[:, 0].contiguous() if k == 1 else Vg)
+    Y2 = Y.unsqueeze(1) if k == 1 else Y
+    sample = torch.arange(0, rows, rows // 24)[:24]
+    # fp64 oracle on the sampled rows, chunked over the columns (the oracle's formula block, bounded memory)
+    Xs = X[blk[sample]].double()
+    ref = torch.zeros(len(sample), k, dtype=torch.float64)
+    for c0 in range(0, n, 250_000):
+        Kc = ko.kernel_block(Xs, X[c0:c0 + 250_000].double(), name, 1.0)
+        ref += Kc @ V[c0:c0 + 250_000].double()
+    err = ko.rel_fro_error(Y2[sample.to(dev)], ref)
+    assert err <= 1e-5, f"{name} n={n} d={d} k={k}: rel err {err:.3e}"
+    # row-partition invariance: the two halves of the block computed separately
+    half = rows // 2
+    top = op.row_oracle(blk[:half]) @ (Vg[:, 0].contiguous() if k == 1 else Vg)
+    assert ko.rel_fro_error(top, Y[:half].double().cpu()) <= 2e-6
+    # linearity in V
+    Yl = op.row_oracle(blk[:half]) @ (2.5 * (Vg[:, 0].contiguous() if k == 1 else Vg))
+    assert ko.rel_fro_error(Yl, 2.5 * top.double().cpu()) <= 2e-6
+
+
 # ------------------------------------------------------------------ raw C ABI
 def test_c_abi_one_shot_and_host_entry(dev):
     """Call the extern "C" entry points directly with raw pointers (what a cgo/JNI/ctypes binding does)."""
