@@ -133,3 +133,33 @@ def test_recurrence_residual_halves_the_products_per_logged_iteration(dev, k):
     # products: sketch (1, plain entry, not counted) + initial residual (1) + per iteration 1 (+1 metric in "true" mode)
     assert n_t == 1 + 1 + 2 * it_t       # init residual, metric at 0, then step + metric per iteration
     assert n_r == 1 + it_r + 1           # init residual, one product per step, one confirming residual
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_fused_edge_shapes(dev, dtype):
+    """Tiny and ragged shapes, the widest reductions (k = gram_cols = 64: 64 KB of shared memory in fp64), an empty
+    column set (the product is an empty sum: only the addend / rhs terms remain), single rows."""
+    from rlaopt_b200 import ops
+
+    tol = 1e-5 if dtype == torch.float32 else 1e-11
+    for n, m, d, k, gc in ((1, 1, 1, 1, 1), (3, 130, 5, 2, 2), (65, 7, 3, 64, 64), (200, 300, 40, 64, 64), (129, 0, 4, 3, 2)):
+        A1, A2 = _rand((n, d), 1).to(dtype), _rand((max(m, 1), d), 2).to(dtype)[:m]
+        V, C, B, L = (_rand(s, i).to(dtype) for i, s in enumerate([(max(m, 1), k), (n, k), (n, k), (n, gc)], start=3))
+        V = V[:m]
+        layout = ops.choose_layout(0, dtype, d, k)
+        c = ops.column_mean(A2.to(dev)) if (layout == ops.LAYOUT_TC and m > 0) else None
+        P1 = ops.pack_points(A1.to(dev), 1.0, None, layout, c)
+        P2 = ops.pack_points(A2.to(dev), 1.0, None, layout, c)
+        Y, G, S = ops.matmat_packed_fused(P1, P2, V.to(dev), "rbf", 2.0, alpha=0.5, addend=C.to(dev), beta=-1.5,
+                                          rhs=B.to(dev), gamma=0.25, gram_with=L.to(dev), want_sqnorm=True)
+        KV = ko.kernel_matmat(A1, A2, V, "rbf", 1.0, 2.0, dtype=torch.float64) if m > 0 else torch.zeros(n, k, dtype=torch.float64)
+        ref = 0.5 * KV - 1.5 * C.double() + 0.25 * B.double()
+        assert Y.shape == (n, k) and G.shape == (gc, k) and S.shape == (k,)
+        assert ko.rel_fro_error(Y, ref) <= tol, (n, m, d, k)
+        assert ko.rel_fro_error(G, L.double().T @ ref) <= 10 * tol and ko.rel_fro_error(S, (ref * ref).sum(0)) <= 10 * tol
+    # beyond the reduction range the C entry refuses instead of computing something else
+    P = ops.pack_points(_rand((10, 3), 9).to(dev), 1.0, None, ops.LAYOUT_SIMT)
+    with pytest.raises(RuntimeError, match="k <= 64"):
+        ops.matmat_packed_fused(P, P, _rand((10, 70), 10).to(dev), "rbf", want_sqnorm=True)
+    with pytest.raises(ValueError, match="rows"):
+        ops.matmat_packed_fused(P, P, _rand((10, 2), 10).to(dev), "rbf", addend=_rand((9, 2), 11).to(dev), beta=1.0)
