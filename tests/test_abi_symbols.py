@@ -144,3 +144,32 @@ def test_torch_library_op_is_registered_from_cpp(lib):
     # the Python-registered twin of round 1 raises the same way
     with pytest.raises(RuntimeError, match="no CPU implementation"):
         torch.ops.rlaopt_b200.kernel_matmat(torch.randn(4, 3), torch.randn(5, 3), torch.randn(5, 2), 0, 1.0, None, 1.0)
+
+
+def test_header_is_plain_c_and_links(lib, tmp_path):
+    """The boundary is a C ABI: ``include/rlaopt_b200.h`` compiles as pedantic C99 (no C++ / torch / CUDA types in the
+    signatures) and a C program links against the shared library and calls a host-only entry point."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    if not os.path.exists(gcc):
+        pytest.skip("no C compiler")
+    from rlaopt_b200 import _lib
+
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "rlaopt_b200.h"\n'
+        "int main(void) {\n"
+        "    rlaopt_b200_epilogue_f32 e = {0};\n"
+        "    (void)e;\n"
+        "    if (rlaopt_b200_layout_supported(RLAOPT_B200_KERNEL_LAPLACE, 4, 32, 16, RLAOPT_B200_LAYOUT_TC)) return 2;\n"
+        "    if (rlaopt_b200_packed_bytes(10, 3, 4, RLAOPT_B200_LAYOUT_SIMT) != 128 * 8 * 4) return 3;\n"
+        "    return rlaopt_b200_abi_version() == RLAOPT_B200_ABI_VERSION ? 0 : 1;\n"
+        "}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    proc = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{os.path.join(ROOT, 'include')}", str(src),
+                           "-o", str(exe), f"-L{libdir}", "-lrlaopt_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
