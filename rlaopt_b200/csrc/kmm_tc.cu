@@ -30,6 +30,8 @@
 #include <stddef.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "kmm_common.cuh"
 #include "kmm_launch.h"
 #include "kmm_tmem_ldst.cuh"
@@ -573,6 +575,7 @@ struct TcParams {
     int64_t ldo, split_stride;
     int64_t n, m;
     int k, kb, nk1, kid;
+    int k_chunks;            // chunks of KP columns of V (gridDim.y, or twice gridDim.y for the two-chunk kernels)
     int a_stages, v_stages;  // smem ring depths (column-tile images / V images + norms)
     int nb, la;              // S/P buffers in TMEM; la = extra V-ring depth (V of tile t is consumed la tiles after its A image)
     int wide;                // 1: d > 192, feature-chunked MMA1 with X and Y K-blocks streamed through the A ring
@@ -673,10 +676,15 @@ __host__ __device__ constexpr uint32_t tc_v_stage_bytes(int kp) { return (uint32
 // image (its N / 2 rows of the B operand) into its own shared memory -- the per-SM ingress that bounds this family
 // (48 KB per 1152 tensor cycles = 42 B/clk, the L2 -> SM limit) is halved.  The peer's epilogue warps arrive on the
 // leader's barriers through the cluster window; two of its idle issue warps relay its "tile landed" barriers.
-template <int KP, int NWG, bool M12, bool WIDE, int KV = 0, int KIDT = -1, bool CG2 = false>
+// DUAL (k > 128): one CTA contracts the SAME P' of a sub-tile with TWO 128-column chunks of V -- S = X.Y^T and the
+// pointwise stage are computed once per 256 columns of V instead of once per 128.  The two O buffers are the two chunks
+// (chunk A drains while MMA2 works on chunk B and vice versa); a thread carries 2 x 64 accumulators, which fits next
+// to the pointwise stage only because that stage re-reads S from TMEM in quarters (the quarter-row epilogue).
+template <int KP, int NWG, bool M12, bool WIDE, int KV = 0, int KIDT = -1, bool CG2 = false, bool DUAL = false>
 __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcParams p) {
     static_assert(KV == 0 || (KV <= 4 && KP == 16 && !WIDE), "register contraction: k <= 4, X resident in TMEM");
     static_assert(!CG2 || (KP == 128 && !WIDE && KV == 0 && NWG == 2), "cta_group::2 is built for the k > 64 family");
+    static_assert(!DUAL || (KP == 128 && NWG == 2 && !WIDE && KV == 0 && !M12 && !CG2), "two chunks per P': k > 128 family");
     constexpr int TC_EPI_WARPS = NWG * 4;
     constexpr int NOB = NWG;  // O buffers: one per epilogue warpgroup (tile u accumulates into O[u % NWG])
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -691,7 +699,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     unsigned char* a_ring = smem;
     unsigned char* v_ring = smem + (size_t)SA * a_stage_bytes;
     float* xchg = reinterpret_cast<float*>(v_ring + (size_t)SV * v_stage_bytes);  // [8][128] per-row tile scales (KP = 128 mode)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 8 * TC_BM);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + (DUAL ? 16 : 8) * TC_BM);  // DUAL: one scale per row, tile and chunk
     uint64_t* a_full = bars;             // [SA] producer -> MMA1
     uint64_t* a_empty = a_full + SA;     // [SA] MMA1 done -> producer
     uint64_t* v_full = a_empty + SA;     // [SV] producer -> MMA2 / epilogue (norms, V scale)
@@ -707,7 +715,8 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_peer + SV);
 
     const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
-    const int kc = blockIdx.y;
+    const int kc = DUAL ? 2 * blockIdx.y : blockIdx.y;  // DUAL: chunks kc and kc + 1 (the second may not exist)
+    const int kc_b = (DUAL && kc + 1 < p.k_chunks) ? kc + 1 : kc;  // an absent second chunk re-reads the first (never stored)
     const int64_t t_begin = (int64_t)blockIdx.z * p.tiles_per_split;
     const int64_t t_end = min(p.sub_tiles, t_begin + (int64_t)p.tiles_per_split);
     const int T = (int)(t_end - t_begin);
@@ -771,6 +780,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         if (lane == 0) {
             const unsigned char* a_src = col_images + (size_t)t_begin * a_img_bytes;
             const unsigned char* v_src = p.vimg + ((size_t)kc * p.sub_tiles + t_begin) * v_img_bytes;
+            const unsigned char* v_src_b = p.vimg + ((size_t)kc_b * p.sub_tiles + t_begin) * v_img_bytes;  // DUAL: second chunk
             int sa = 0, sv = 0;
             uint32_t pha = 1, phv = 1;  // a fresh barrier passes a wait on parity 1
             const uint32_t crank = p.pair ? cluster_ctarank() : 0;
@@ -884,6 +894,21 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                         bulk_copy_g2s_mc(vdst + v_half, v_src + v_half, v_img_bytes - v_half, &v_full[sv], 3);
                     }
                 }
+                if constexpr (DUAL) {
+                    // the record of the second chunk of this sub-tile goes to the next V-ring stage
+                    if (++sv == SV) {
+                        sv = 0;
+                        phv ^= 1;
+                    }
+                    mbar_wait(&v_empty[sv], phv);
+                    unsigned char* vdst = v_ring + (size_t)sv * v_stage_bytes;
+                    mbar_arrive_expect_tx(&v_full[sv], v_img_bytes);
+                    constexpr uint32_t v_half = KP * 128;
+                    if (!p.pair) bulk_copy_g2s(vdst, v_src_b, v_img_bytes, &v_full[sv]);
+                    else if (crank == 0) bulk_copy_g2s_mc(vdst, v_src_b, v_half, &v_full[sv], 3);
+                    else bulk_copy_g2s_mc(vdst + v_half, v_src_b + v_half, v_img_bytes - v_half, &v_full[sv], 3);
+                    v_src_b += v_img_bytes;
+                }
                 }
                 a_src += a_img_bytes;
                 v_src += v_img_bytes;
@@ -959,9 +984,10 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         auto issue_mma2 = [&](int b, int ob, int s) {
             const uint32_t d_t = tmem + col_o + ob * KP;
             // P' layout in the S/P buffer: hi pairs in columns [0, 32), lo pairs in [32, 64); the quarter-row epilogue
-            // (NWG = 4) interleaves them per 16 entries: hi of K-step ks at 16 ks, lo at 16 ks + 8
-            constexpr uint32_t p_step = NWG == 4 ? 16 : 8;
-            const uint32_t p_hi = tmem + col_sp + b * 64, p_lo = p_hi + (NWG == 4 ? 8 : 32);
+            // (NWG = 4, DUAL) interleaves them per 16 entries: hi of K-step ks at 16 ks, lo at 16 ks + 8
+            constexpr bool interleaved = NWG == 4 || DUAL;
+            constexpr uint32_t p_step = interleaved ? 16 : 8;
+            const uint32_t p_hi = tmem + col_sp + b * 64, p_lo = p_hi + (interleaved ? 8 : 32);
             const uint32_t img = v_ring_base + (uint32_t)s * v_stage_bytes;
             const uint32_t dlo_hi = desc_lo0 + (img >> 4);
             const uint32_t dlo_lo = desc_lo0 + ((img + v_lo_off) >> 4);
@@ -1111,6 +1137,35 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                         phv ^= 1;
                     }
                 }
+            } else if constexpr (DUAL) {
+                // ---- two chunks per sub-tile: O[0] = P'[b] . V'_A, O[1] = P'[b] . V'_B; P'[b] is released after both ----
+                int b2 = 0, sv = 0;
+                uint32_t use2 = 0, phv = 0;
+                for (int u = 0; u < T; ++u) {
+                    const uint32_t opar = (uint32_t)(u & 1);  // each O buffer is used once per sub-tile
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        // P written (first chunk); V record landed; O[c] of the previous sub-tile has been drained
+                        if (c == 0) mbar_wait3(&p_full[b2], use2, &v_full[sv], phv, &o_free[c], opar ^ 1);
+                        else mbar_wait2(&v_full[sv], phv, &o_free[c], opar ^ 1);
+                        tc_fence_after();
+                        issue_mma2(b2, c, sv);
+                        if (elect_one()) {
+                            commit_bar(&v_empty[sv], true);
+                            if (c == 1) commit_bar(&p_free[b2], false);
+                            commit_bar(&o_full[c], false);
+                        }
+                        __syncwarp();
+                        if (++sv == SV) {
+                            sv = 0;
+                            phv ^= 1;
+                        }
+                    }
+                    if (++b2 == NB) {
+                        b2 = 0;
+                        use2 ^= 1;
+                    }
+                }
             } else {
             int b2 = 0, sv = 0;
             uint32_t use2 = 0, phv = 0;
@@ -1195,15 +1250,19 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         // so a thread still carries 64 accumulators; the owner publishes the tile's scale through smem.
         constexpr bool SPLIT = KP > 64;
         constexpr bool FRAG = KV > 0 && !M12;
-        constexpr bool QUART = NWG == 4;  // quarter-row epilogue of the four-warpgroup instantiations (KP <= 32, not Matern-1/2)
-        static_assert(!QUART || (KV == 0 && !SPLIT && !M12 && !WIDE), "four epilogue warpgroups: small-d/k families only");
-        constexpr int DW = SPLIT ? KP / 2 : KP;  // O columns one thread accumulates
-        uint64_t acc[DW / 2];                    // fp32 pairs
+        // quarter-row epilogue (S re-read from TMEM in pieces): the four-warpgroup instantiations and the two-chunk kernels
+        constexpr bool QUART = NWG == 4 || DUAL;
+        static_assert(!QUART || (KV == 0 && !M12 && !WIDE), "quarter-row epilogue: X-resident MMA2 kernels, not Matern-1/2");
+        constexpr int DW = SPLIT ? KP / 2 : KP;  // O columns one thread accumulates (per chunk)
+        constexpr int NCH = DUAL ? 2 : 1;        // chunks of V contracted with the same P'
+        uint64_t acc[NCH * DW / 2];              // fp32 pairs
 #pragma unroll
-        for (int c = 0; c < DW / 2; ++c) acc[c] = 0ull;
+        for (int c = 0; c < NCH * DW / 2; ++c) acc[c] = 0ull;
 
-        // acc += O[ob] * dsc: one sub-tile's accumulator, un-scaled and added with round-to-nearest
-        auto drain = [&](int ob, uint32_t par, float dsc, const float* dsc_ptr = nullptr) {
+        // acc += O[ob] * dsc: one sub-tile's accumulator, un-scaled and added with round-to-nearest; CH (compile time):
+        // which half of the accumulators (the chunk) it goes to
+        auto drain = [&](auto CH, int ob, uint32_t par, float dsc, const float* dsc_ptr = nullptr) {
+            constexpr int aoff = decltype(CH)::value * (DW / 2);
             mbar_wait(&o_full[ob], par);
             tc_fence_after();
             if (dsc_ptr) dsc = *dsc_ptr;
@@ -1219,20 +1278,27 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             for (int l = 0; l < NLD; ++l)
 #pragma unroll
                 for (int e = 0; e < W / 2; ++e)
-                    acc[l * (W / 2) + e] = fma2(pack2(__uint_as_float(o[l][2 * e]), __uint_as_float(o[l][2 * e + 1])), d2,
-                                                acc[l * (W / 2) + e]);
+                    acc[aoff + l * (W / 2) + e] = fma2(pack2(__uint_as_float(o[l][2 * e]), __uint_as_float(o[l][2 * e + 1])), d2,
+                                                       acc[aoff + l * (W / 2) + e]);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) arrive_pair(&o_free[ob]);
         };
-        float* dsc_sm = xchg;  // [8][128]: per-row un-scale factors of the last 8 tiles (SPLIT mode)
+        constexpr std::integral_constant<int, 0> CH0{};
+        constexpr std::integral_constant<int, NCH - 1> CH1{};
+        float* dsc_sm = xchg;  // [8][128]([2] DUAL): per-row un-scale factors of the last 8 tiles (SPLIT mode)
         int next_drain = 0;    // SPLIT mode: next tile this warpgroup has to drain
         auto drain_through = [&](int last) {  // SPLIT mode: drain tiles next_drain .. last (inclusive)
             for (; next_drain <= last; ++next_drain) {
                 const int t = next_drain;
                 // the owner's scale is read inside drain(), after its wait on o_full (published before p_full ->
                 // MMA2 -> o_full): one barrier poll per drain, not two (a successful poll costs ~100 cycles)
-                drain(t % NOB, (uint32_t)((t / NOB) & 1), -1.0f, &dsc_sm[(t & 7) * TC_BM + row]);
+                if constexpr (DUAL) {  // O[0] / O[1] are the two chunks of tile t, each used once per tile
+                    drain(CH0, 0, (uint32_t)(t & 1), -1.0f, &dsc_sm[((t & 7) * TC_BM + row) * 2]);
+                    drain(CH1, 1, (uint32_t)(t & 1), -1.0f, &dsc_sm[((t & 7) * TC_BM + row) * 2 + 1]);
+                } else {
+                    drain(CH0, t % NOB, (uint32_t)((t / NOB) & 1), -1.0f, &dsc_sm[(t & 7) * TC_BM + row]);
+                }
             }
         };
 
@@ -1272,10 +1338,19 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
         }
         TC_PROF_DECL
         for (int u = g; u < T; u += NWG) {
+            int sv_b = 0;  // DUAL: the V-ring stages of sub-tile u are 2 u (first chunk) and 2 u + 1 (second chunk)
+            uint32_t phv_b = 0;
+            if constexpr (DUAL) {
+                sv = (2 * u) % SV;
+                phv = (uint32_t)(((2 * u) / SV) & 1);
+                sv_b = (2 * u + 1) % SV;
+                phv_b = (uint32_t)(((2 * u + 1) / SV) & 1);
+            }
             const unsigned char* vst = v_ring + (size_t)sv * v_stage_bytes;
             TC_PROF(7)
             // |y|^2 and the V scale of this sub-tile are in smem; MMA1 has written S[b]
-            mbar_wait2(&v_full[sv], phv, &s_full[b], use);
+            if constexpr (DUAL) mbar_wait3(&v_full[sv], phv, &v_full[sv_b], phv_b, &s_full[b], use);
+            else mbar_wait2(&v_full[sv], phv, &s_full[b], use);
             TC_PROF(1)
             tc_fence_after();
             const uint32_t t_s = tmem + lane_bits + col_sp + b * 64;
@@ -1364,9 +1439,16 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                 }
                 tmem_wait_st();
                 tc_fence_before();
+                if constexpr (DUAL) {  // per-chunk un-scale factors (the V images of the two chunks carry their own scales)
+                    const float vinv_b = *reinterpret_cast<const float*>(v_ring + (size_t)sv_b * v_stage_bytes + KP * 256);
+                    const float e2 = __uint_as_float((uint32_t)(127 - E) << 23);
+                    dsc_sm[((u & 7) * TC_BM + row) * 2] = dsc;  // published before p_full -> MMA2 -> o_full
+                    dsc_sm[((u & 7) * TC_BM + row) * 2 + 1] = e2 * vinv_b;
+                }
                 __syncwarp();
                 if (lane == 0) arrive_pair(&p_full[b]);
-                if (u >= NWG) drain(g, (uint32_t)(((u - NWG) / NWG) & 1), dsc_prev);
+                if constexpr (DUAL) drain_through(u - 1);
+                else if (u >= NWG) drain(CH0, g, (uint32_t)(((u - NWG) / NWG) & 1), dsc_prev);
                 dsc_prev = dsc;
             } else {
             uint32_t s0[32], s1[32];
@@ -1561,7 +1643,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
                 if (lane == 0) mbar_arrive(&p_full[b]);
                 TC_PROF(4)
                 if (SPLIT) drain_through(u - 1);
-                else if (u >= NWG) drain(g, (uint32_t)(((u - NWG) / NWG) & 1), 1.0f);
+                else if (u >= NWG) drain(CH0, g, (uint32_t)(((u - NWG) / NWG) & 1), 1.0f);
                 TC_PROF(5)
             } else {
             // ---- pass 1: z_j and the row extreme ----
@@ -1697,7 +1779,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             TC_PROF(4)
             // drain finished sub-tiles while the tensor core works on this one
             if (SPLIT) drain_through(u - 1);
-            else if (u >= NWG) drain(g, (uint32_t)(((u - NWG) / NWG) & 1), dsc_prev);
+            else if (u >= NWG) drain(CH0, g, (uint32_t)(((u - NWG) / NWG) & 1), dsc_prev);
             TC_PROF(5)
             dsc_prev = dsc;
             }
@@ -1764,7 +1846,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             drain_through(T - 1);
         } else {
             const int last = ((T - 1 - g) / NWG) * NWG + g;  // this warpgroup's last tile (T > g)
-            if (T > g) drain(g, (uint32_t)((last / NWG) & 1), TC_DIAG(2) ? 1.0f : dsc_prev);
+            if (T > g) drain(CH0, g, (uint32_t)((last / NWG) & 1), TC_DIAG(2) ? 1.0f : dsc_prev);
         }
 
         if (SPLIT) {
@@ -1772,12 +1854,16 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             if (grow < p.n) {
                 float* dst = p.out + (int64_t)blockIdx.z * p.split_stride + grow * p.ldo;
 #pragma unroll
-                for (int c = 0; c < DW / 2; ++c) {
-                    const int col = kc * KP + g * DW + 2 * c;
-                    float y0, y1;
-                    unpack2(acc[c], y0, y1);
-                    if (col < p.k) dst[col] = y0 * p.scale_out;
-                    if (col + 1 < p.k) dst[col + 1] = y1 * p.scale_out;
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if (ch == 1 && kc_b == kc) break;  // DUAL: the second chunk does not exist (odd number of chunks)
+#pragma unroll
+                    for (int c = 0; c < DW / 2; ++c) {
+                        const int col = (kc + ch) * KP + g * DW + 2 * c;
+                        float y0, y1;
+                        unpack2(acc[ch * (DW / 2) + c], y0, y1);
+                        if (col < p.k) dst[col] = y0 * p.scale_out;
+                        if (col + 1 < p.k) dst[col + 1] = y1 * p.scale_out;
+                    }
                 }
             }
         } else {
@@ -1825,7 +1911,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
 }
 
 struct TcPlan {
-    int kb, kp, k_chunks, a_stages, v_stages, nb, la, nwg, wide, splits, tiles_per_split, pair, kv, cg2;
+    int kb, kp, k_chunks, a_stages, v_stages, nb, la, nwg, wide, splits, tiles_per_split, pair, kv, cg2, dual;
     int64_t sub_tiles;
     size_t smem_bytes, vimg_bytes, part_bytes;
 };
@@ -1872,7 +1958,18 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     la = max(1, min(nb >= 3 ? nb - 2 : 1, tc_env_int("RLAOPT_B200_TC_LA", la)));
     // smem: A ring (column-tile images) + V ring (la stages deeper: V of tile t is consumed la tiles after its A)
     const size_t a_stage = wide ? (size_t)TC_WIDE_STAGE_BYTES : tc_image_bytes(kb), v_stage = tc_v_stage_bytes(kp);
-    const size_t fixed = 8 * TC_BM * sizeof(float) + 64 * sizeof(uint64_t) + 64;
+    // k > 128: two 128-column chunks of V per S / P' (the DUAL instantiations; every kernel but Matern-1/2, whose near-pair
+    // recompute holds the whole row; the kernel id is known at launch -- sizing queries see the same workspace either way).
+    // Measured (profiles/r02_tc_dual_ab.log): it pays where S is expensive -- 64 < d <= 128: RBF d=128 k=256 362 -> 413
+    // Gentries/s -- and loses for d <= 64 (k=1000 133 -> 109, Matern-5/2 d=32 k=200 551 -> 396): the two O buffers are
+    // then the two chunks of ONE sub-tile, so a buffer is reused after one sub-tile instead of two and MMA2 waits for a
+    // warpgroup that is still in its (long) pointwise stage.  RLAOPT_B200_TC_DUAL: 1 = where it pays (default), 0 = never,
+    // 2 = wherever it is possible.
+    const int dual_env = tc_env_int("RLAOPT_B200_TC_DUAL", 1);
+    bool dual = kp == 128 && !wide && k > 128 && kid >= 0 && kid != KID_MATERN12 && (dual_env >= 2 || (dual_env == 1 && kb >= 2)) &&
+                !tc_env_int("RLAOPT_B200_TC_CG2", 0);
+    size_t fixed = 8 * TC_BM * sizeof(float) + 64 * sizeof(uint64_t) + 64;
+    if (dual) fixed += 8 * TC_BM * sizeof(float);  // one un-scale factor per row, tile and chunk
     // ring depth: 4 stages; deeper rings measured no gain even at one sub-tile per ~600 cycles (RLAOPT_B200_TC_SA)
     int sa = tc_env_int("RLAOPT_B200_TC_SA", 4), sv;
     if (sa < 2) sa = 2;
@@ -1884,6 +1981,15 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     } else {
         while (sa > 2 && sa * a_stage + (sa + la) * v_stage + fixed > (size_t)TC_SMEM_LIMIT) --sa;
         sv = sa + la;
+        if (dual) {  // a sub-tile consumes two V records: at least two sub-tiles in flight
+            if (sv < 4) sv = 4;
+            while (sa > 2 && sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) --sa;
+            if (sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) {
+                dual = false;
+                fixed -= 8 * TC_BM * sizeof(float);
+                sv = sa + la;
+            }
+        }
     }
     if (sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) return false;
     if (3 * sa + 3 * sv + 3 * nb + 2 * nwg + 1 > 64) return false;  // mbarriers (incl. the CG2 relay barriers) fit the array
@@ -1913,6 +2019,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
         if (pl->cg2) pl->pair = 1;
     }
     pl->kv = kv;
+    pl->dual = dual ? 1 : 0;
     pl->smem_bytes = sa * a_stage + sv * v_stage + fixed;
     const int64_t base = ((n + TC_BM - 1) / TC_BM) * pl->k_chunks;
     const int64_t target = (int64_t)sm_count * 2;
@@ -1988,15 +2095,15 @@ size_t tc_workspace_bytes(int64_t n, int64_t m, int64_t d, int64_t k, int sm_cou
     return round_up((int64_t)pl.vimg_bytes, 256) + part;
 }
 
-template <int KP, int NWG, bool M12, bool WIDE, int KV = 0, int KIDT = -1, bool CG2 = false>
+template <int KP, int NWG, bool M12, bool WIDE, int KV = 0, int KIDT = -1, bool CG2 = false, bool DUAL = false>
 static cudaError_t launch_tc_inst(const TcParams& p, const TcPlan& pl, int64_t n, cudaStream_t stream) {
-    auto kern = kmm_tc_kernel<KP, NWG, M12, WIDE, KV, KIDT, CG2>;
+    auto kern = kmm_tc_kernel<KP, NWG, M12, WIDE, KV, KIDT, CG2, DUAL>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (err != cudaSuccess) return err;
     unsigned row_blocks = (unsigned)((n + TC_BM - 1) / TC_BM);
     if (p.pair) row_blocks = (row_blocks + 1) & ~1u;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(row_blocks, (unsigned)pl.k_chunks, (unsigned)pl.splits);
+    cfg.gridDim = dim3(row_blocks, (unsigned)(pl.dual ? (pl.k_chunks + 1) / 2 : pl.k_chunks), (unsigned)pl.splits);
     cfg.blockDim = dim3(tc_threads(NWG));
     cfg.dynamicSmemBytes = pl.smem_bytes;
     cfg.stream = stream;
@@ -2023,6 +2130,13 @@ static cudaError_t launch_tc_kp(const TcParams& p, const TcPlan& pl, int64_t n, 
         }
     }
     if constexpr (KP == 128) {
+        if (pl.dual) {  // k > 128: two chunks of V per P'
+            switch (p.kid) {
+                case KID_RBF: return launch_tc_inst<KP, NWG, false, false, 0, KID_RBF, false, true>(p, pl, n, stream);
+                case KID_MATERN32: return launch_tc_inst<KP, NWG, false, false, 0, KID_MATERN32, false, true>(p, pl, n, stream);
+                default: return launch_tc_inst<KP, NWG, false, false, 0, KID_MATERN52, false, true>(p, pl, n, stream);
+            }
+        }
         if (pl.cg2) {  // CTA pairs with cta_group::2 MMAs
             switch (p.kid) {
                 case KID_RBF: return launch_tc_inst<KP, NWG, false, false, 0, KID_RBF, true>(p, pl, n, stream);
@@ -2109,6 +2223,7 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     p.n = n;
     p.m = m;
     p.k = (int)k;
+    p.k_chunks = pl.k_chunks;
     p.kb = pl.kb;
     p.nk1 = (int)((d + 15) / 16);
     p.a_stages = pl.a_stages;

@@ -321,3 +321,26 @@ def test_register_contraction_long_positive_sum_and_tiny_values(dev):
     # guard sends these rows to the direct-difference kernel and the 1e-5 bar holds (values ~1e-30)
     got = kernel_matmat(far.to(dev), A2[:5000].to(dev), V[:5000].to(dev), "rbf", 1.0)
     assert ko.rel_fro_error(got, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["rbf", "matern32", "matern52", "matern12"])
+@pytest.mark.parametrize("n,m,d,k", [(300, 1000, 64, 130), (129, 257, 16, 256), (1000, 5000, 128, 257), (260, 700, 33, 1000),
+                                     (513, 129, 100, 300), (40000, 300, 8, 384), (77, 64 * 40 + 3, 64, 129)])
+def test_two_chunks_per_sub_tile_family(dev, name, n, m, d, k, monkeypatch):
+    """k > 128: one CTA contracts the same P' with two 128-column chunks of V (DUAL instantiations; Matern-1/2 keeps one
+    chunk per CTA).  Odd chunk counts, ragged last chunks, single sub-tiles, column splits; against the fp64 oracle and
+    against the one-chunk kernels on the same inputs."""
+    from rlaopt_b200._lib import LAYOUT_TC
+    from rlaopt_b200.ops import kernel_matmat
+
+    A1, A2 = _rand((n, d), 61) / d**0.5, _rand((m, d), 62) / d**0.5
+    V = _rand((m, k), 63)
+    ref = ko.kernel_matmat_gemm_form(A1, A2, V, name, 1.1, 0.9, dtype=torch.float64)
+    outs = []
+    for dual in ("2", "0"):  # 2 = wherever possible (the default uses it for 64 < d <= 128 only), 0 = never
+        monkeypatch.setenv("RLAOPT_B200_TC_DUAL", dual)
+        got = kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), name, 1.1, 0.9, layout=LAYOUT_TC)
+        assert got.shape == (n, k)
+        assert ko.rel_fro_error(got, ref) <= 1e-5, (name, n, m, d, k, dual)
+        outs.append(got)
+    assert ko.rel_fro_error(outs[0], outs[1].double().cpu()) <= 2e-6
