@@ -576,6 +576,8 @@ struct TcParams {
     int64_t n, m;
     int k, kb, nk1, kid;
     int k_chunks;            // chunks of KP columns of V (gridDim.y, or twice gridDim.y for the two-chunk kernels)
+    int dual_mode;           // two-chunk kernels: 1 = drains after the pointwise stage, 2 = pointwise stage sliced between the drains
+    int dual_overlap;        // sliced mode: 1 = the quarter's loads overlap the drain's (A/B knob)
     int a_stages, v_stages;  // smem ring depths (column-tile images / V images + norms)
     int nb, la;              // S/P buffers in TMEM; la = extra V-ring depth (V of tile t is consumed la tiles after its A image)
     int wide;                // 1: d > 192, feature-chunked MMA1 with X and Y K-blocks streamed through the A ring
@@ -699,7 +701,8 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
     unsigned char* a_ring = smem;
     unsigned char* v_ring = smem + (size_t)SA * a_stage_bytes;
     float* xchg = reinterpret_cast<float*>(v_ring + (size_t)SV * v_stage_bytes);  // [8][128] per-row tile scales (KP = 128 mode)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + (DUAL ? 16 : 8) * TC_BM);  // DUAL: one scale per row, tile and chunk
+    // DUAL: one scale per row, tile and chunk, then [2 warpgroups][2][128] floats of column norms + V scales (dual_mode 2)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + (DUAL ? 16 * TC_BM + 512 : 8 * TC_BM));
     uint64_t* a_full = bars;             // [SA] producer -> MMA1
     uint64_t* a_empty = a_full + SA;     // [SA] MMA1 done -> producer
     uint64_t* v_full = a_empty + SA;     // [SV] producer -> MMA2 / epilogue (norms, V scale)
@@ -1146,6 +1149,9 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         // P written (first chunk); V record landed; O[c] of the previous sub-tile has been drained
+                        // bit 16 (sliced mode, early announcement): chunk A of sub-tile u is issued only after chunk B of
+                        // sub-tile u - 1 has COMPLETED (the issuer itself waits for its completion barrier)
+                        if (c == 0 && u > 0 && (p.dual_overlap & 16)) mbar_wait(&o_full[1], (uint32_t)((u - 1) & 1));
                         if (c == 0) mbar_wait3(&p_full[b2], use2, &v_full[sv], phv, &o_free[c], opar ^ 1);
                         else mbar_wait2(&v_full[sv], phv, &o_free[c], opar ^ 1);
                         tc_fence_after();
@@ -1336,8 +1342,236 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
 #pragma unroll
             for (int c = 0; c < (KV ? KV : 1); ++c) accf[r][c] = accf2[r][c] = 0.0f;
         }
+        bool sliced = false;
+        if constexpr (DUAL) {
+            if (p.dual_mode == 2) {
+                // ---- sliced two-chunk epilogue (three S/P buffers) ----
+                // With the drains behind the pointwise stage (dual_mode 1) MMA2 of sub-tile t + 1 waits for the owner of
+                // sub-tile t + 2, which sits in its ~1800-cycle pointwise stage and cannot drain O of sub-tile t.  Here both
+                // warpgroups walk ALL sub-tiles, drain chunk A, then chunk B of each as soon as it completes, and fill the two
+                // gaps with a quarter of the pointwise stage of the warpgroup's NEXT own sub-tile: tile u is prepared in the
+                // slots of tiles u - 2 (row extreme + quarter 0, quarter 1) and u - 1 (quarters 2, 3, publish).  The column
+                // norms and V scales of tile u come from global memory (the V ring only feeds MMA2): prefetched one own
+                // tile ahead into a register, handed to the warpgroup through a double-buffered smem row.
+                sliced = true;
+                float* wny = xchg + 16 * TC_BM + g * 256;
+                const unsigned char* rec_a = p.vimg + ((size_t)kc * p.sub_tiles + t_begin) * v_img_bytes;
+                const unsigned char* rec_b = p.vimg + ((size_t)kc_b * p.sub_tiles + t_begin) * v_img_bytes;
+                float pre = 0.0f;
+                auto prefetch = [&](int u) {
+                    if (u < T && row < 66) {
+                        const unsigned char* ra = rec_a + (size_t)u * v_img_bytes;
+                        if (row < 64) pre = __ldg(reinterpret_cast<const float*>(ra + v_norm_off) + row);
+                        else if (row == 64) pre = __ldg(reinterpret_cast<const float*>(ra + KP * 256));
+                        else pre = __ldg(reinterpret_cast<const float*>(rec_b + (size_t)u * v_img_bytes + KP * 256));
+                    }
+                };
+                const uint64_t nl2 = pack2(-TC_LOG2E, -TC_LOG2E), one2 = pack2(1.0f, 1.0f),
+                               third2 = pack2(1.0f / 3.0f, 1.0f / 3.0f);
+                uint64_t E2 = 0ull;
+                int Ecur = 0;
+                int pending_pfull = -1;  // diagnostic (bit 8): p_full arrive deferred to the next slot
+                // 16 entries of S -> P'_hi (8 words) | P'_lo (8 words), written in place
+                auto quarter = [&](const uint32_t* s16, const float4* ny4p, uint32_t t_dst) {
+                    uint32_t pq[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 ny4 = ny4p[i];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const uint64_t zz = fma2(pack2(__uint_as_float(s16[4 * i + 2 * e]), __uint_as_float(s16[4 * i + 2 * e + 1])),
+                                                     za2, fma2(e == 0 ? pack2(ny4.x, ny4.y) : pack2(ny4.z, ny4.w), zc2, zx2));
+                            float p0, p1;
+                            if (is_rbf) {
+                                float a0, a1;
+                                unpack2(add2(zz, E2), a0, a1);
+                                p0 = ex2_approx(a0);
+                                p1 = ex2_approx(a1);
+                            } else {
+                                float z0, z1;
+                                unpack2(zz, z0, z1);
+                                const uint64_t r2 = pack2(sqrt_approx(fmaxf(z0, 0.0f)), sqrt_approx(fmaxf(z1, 0.0f)));
+                                float a0, a1;
+                                unpack2(fma2(r2, nl2, E2), a0, a1);
+                                uint64_t pp = pack2(ex2_approx(a0), ex2_approx(a1));
+                                if (kid == KID_MATERN32) pp = mul2(pp, add2(r2, one2));
+                                else pp = mul2(pp, fma2(r2, fma2(r2, third2, one2), one2));
+                                unpack2(pp, p0, p1);
+                            }
+                            const __half2 h2 = __floats2half2_rn(p0, p1);
+                            const float2 f2 = __half22float2(h2);
+                            float l0, l1;
+                            unpack2(sub2(pack2(p0, p1), pack2(f2.x, f2.y)), l0, l1);
+                            const __half2 l2 = __floats2half2_rn(l0, l1);
+                            pq[2 * i + e] = *reinterpret_cast<const uint32_t*>(&h2);
+                            pq[8 + 2 * i + e] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                    }
+                    tmem_st16(t_dst, pq);
+                };
+                auto pw_slice = [&](int u, auto SL) {
+                    constexpr int sl = decltype(SL)::value;
+                    if (u < 0 || u >= T) return;
+                    const int bu = u % NB;
+                    const uint32_t t_s = tmem + lane_bits + col_sp + bu * 64;
+                    float* nys = wny + ((u >> 1) & 1) * 128;
+                    const bool bypass = (p.dual_overlap & 2) != 0;  // diagnostic: norms straight from global memory
+                    const float* ny = bypass ? reinterpret_cast<const float*>(rec_a + (size_t)u * v_img_bytes + v_norm_off) : nys;
+                    const float4* nyq = reinterpret_cast<const float4*>(ny);
+                    if constexpr (sl == 0) {
+                        if (row < 66) nys[row] = pre;
+                        asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+                        prefetch(u + 2);
+                        mbar_wait(&s_full[bu], (uint32_t)((u / NB) & 1));
+                        tc_fence_after();
+                        uint32_t s0[32], s1[32];
+                        tmem_ld32(t_s, s0);
+                        tmem_ld32(t_s + 32, s1);
+                        tmem_wait_ld();
+                        float ext = is_rbf ? -3.0e38f : 3.0e38f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float4 ny4 = nyq[i];
+                            const uint32_t* sh = i < 8 ? &s0[4 * i] : &s1[4 * (i - 8)];
+                            float z0, z1, z2, z3;
+                            unpack2(fma2(pack2(__uint_as_float(sh[0]), __uint_as_float(sh[1])), za2,
+                                         fma2(pack2(ny4.x, ny4.y), zc2, zx2)), z0, z1);
+                            unpack2(fma2(pack2(__uint_as_float(sh[2]), __uint_as_float(sh[3])), za2,
+                                         fma2(pack2(ny4.z, ny4.w), zc2, zx2)), z2, z3);
+                            if (is_rbf) ext = fmaxf(max3(ext, z0, z1), fmaxf(z2, z3));
+                            else ext = fminf(min3(ext, z0, z1), fminf(z2, z3));
+                        }
+                        int E;
+                        if (is_rbf) {
+                            E = 14 - __float2int_rd(fmaxf(ext, -200.0f));
+                        } else {
+                            float pmax;
+                            if (kid == KID_MATERN32) pmax = tc_value<KID_MATERN32>(ext);
+                            else pmax = tc_value<KID_MATERN52>(ext);
+                            E = 14 + 127 - (int)((__float_as_uint(pmax) >> 23) & 0xFF);
+                        }
+                        E = max(0, min(E, 120));
+                        Ecur = E;
+                        const float Ef = (float)E;
+                        E2 = pack2(Ef, Ef);
+                        quarter(s0, nyq, t_s);
+                    } else {
+                        uint32_t sq[16];
+                        tmem_ld16(t_s + sl * 16, sq);
+                        tmem_wait_ld();
+                        quarter(sq, nyq + sl * 4, t_s + sl * 16);
+                    }
+                    if constexpr (sl == 3) {
+                        tmem_wait_st();
+                        tc_fence_before();
+                        const float e2 = __uint_as_float((uint32_t)(127 - Ecur) << 23);
+                        dsc_sm[((u & 7) * TC_BM + row) * 2] = e2 * nys[64];  // published before p_full -> MMA2 -> o_full
+                        dsc_sm[((u & 7) * TC_BM + row) * 2 + 1] = e2 * nys[65];
+                        __syncwarp();
+                        if (p.dual_overlap & 8) pending_pfull = bu;
+                        else if (lane == 0) arrive_pair(&p_full[bu]);
+                    }
+                };
+                constexpr std::integral_constant<int, 0> S0{};
+                constexpr std::integral_constant<int, 1> S1{};
+                constexpr std::integral_constant<int, 2> S2{};
+                constexpr std::integral_constant<int, 3> S3{};
+                prefetch(g);
+                // t = -2, -1: the slots of the sub-tiles "before the first" prepare tiles 0 and 1 (nothing to drain yet)
+                // one slot: drain chunk CH of sub-tile t, then work item WK of sub-tile u:
+                //   0: row extreme + quarter 0    1: quarters 1 and 2    2: quarter 3 + publish (p_full)    3: nothing
+                // P'(u) must be complete while MMA2 of chunk B of sub-tile u - 1 still runs, or the tensor pipe idles for a
+                // whole slot: so the last item sits in slot A of sub-tile u - 1 and slot B of a foreign sub-tile only drains.
+                // Items 1 and 2 overlap the drain: the quarter's S load and the first half of O are in flight together, the
+                // second half of O loads while the quarter runs through the special-function pipe.
+                auto slot = [&](auto CH, int t, int u, auto WK) {
+                    constexpr int wk = decltype(WK)::value;
+                    constexpr int ch = decltype(CH)::value;
+                    const bool have_pw = wk != 3 && u >= 0 && u < T;
+                    if (pending_pfull >= 0) {  // diagnostic: P'(u) is announced only once chunk B of sub-tile u - 1 has completed
+                        if (t >= 0) mbar_wait(&o_full[ch], (uint32_t)(t & 1));
+                        __syncwarp();
+                        if (lane == 0) arrive_pair(&p_full[pending_pfull]);
+                        pending_pfull = -1;
+                    }
+                    if (wk == 0 || wk >= 3 || t < 0 || !have_pw || (p.dual_overlap & 1) == 0) {
+                        if (t >= 0) drain(CH, ch, (uint32_t)(t & 1), -1.0f, &dsc_sm[((t & 7) * TC_BM + row) * 2 + ch]);
+                        if (have_pw) {
+                            if constexpr (wk == 0) pw_slice(u, S0);
+                            if constexpr (wk == 1) {
+                                pw_slice(u, S1);
+                                pw_slice(u, S2);
+                            }
+                            if constexpr (wk == 2) pw_slice(u, S3);
+                            if constexpr (wk == 4) pw_slice(u, S1);
+                            if constexpr (wk == 5) pw_slice(u, S2);
+                        }
+                        return;
+                    }
+                    constexpr int sl = wk == 1 ? 1 : 3;
+                    const int bu = u % NB;
+                    const uint32_t t_s = tmem + lane_bits + col_sp + bu * 64;
+                    const float* nys = wny + ((u >> 1) & 1) * 128;
+                    const float* ny = (p.dual_overlap & 2) ? reinterpret_cast<const float*>(rec_a + (size_t)u * v_img_bytes + v_norm_off) : nys;
+                    uint32_t sq[16];
+                    tmem_ld16(t_s + sl * 16, sq);
+                    mbar_wait(&o_full[ch], (uint32_t)(t & 1));
+                    tc_fence_after();
+                    const float dsc = dsc_sm[((t & 7) * TC_BM + row) * 2 + ch];
+                    const uint64_t d2 = pack2(dsc, dsc);
+                    const uint32_t t_o = tmem + lane_bits + col_o + ch * KP + g * DW;
+                    constexpr int aoff = ch * (DW / 2);
+                    uint32_t o1[32], o2[32];
+                    tmem_ld32(t_o, o1);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        acc[aoff + e] = fma2(pack2(__uint_as_float(o1[2 * e]), __uint_as_float(o1[2 * e + 1])), d2, acc[aoff + e]);
+                    tmem_ld32(t_o + 32, o2);
+                    quarter(sq, reinterpret_cast<const float4*>(ny) + sl * 4, t_s + sl * 16);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        acc[aoff + 16 + e] = fma2(pack2(__uint_as_float(o2[2 * e]), __uint_as_float(o2[2 * e + 1])), d2, acc[aoff + 16 + e]);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) arrive_pair(&o_free[ch]);
+                    if constexpr (wk == 1) pw_slice(u, S2);
+                    if constexpr (wk == 2) {
+                        tmem_wait_st();
+                        tc_fence_before();
+                        const float e2 = __uint_as_float((uint32_t)(127 - Ecur) << 23);
+                        dsc_sm[((u & 7) * TC_BM + row) * 2] = e2 * nys[64];
+                        dsc_sm[((u & 7) * TC_BM + row) * 2 + 1] = e2 * nys[65];
+                        __syncwarp();
+                        if (p.dual_overlap & 8) pending_pfull = bu;
+                        else if (lane == 0) arrive_pair(&p_full[bu]);
+                    }
+                };
+                constexpr std::integral_constant<int, 4> S4{};
+                constexpr std::integral_constant<int, 5> S5{};
+                for (int t = -2; t < T; ++t) {
+                    if (p.dual_overlap & 4) {  // diagnostic: one quarter per slot, publish in slot B of sub-tile u - 1
+                        if ((t & 1) == g) {
+                            slot(CH0, t, t + 2, S0);
+                            slot(CH1, t, t + 2, S4);
+                        } else {
+                            slot(CH0, t, t + 1, S5);
+                            slot(CH1, t, t + 1, S2);
+                        }
+                    } else if ((t & 1) == g) {
+                        slot(CH0, t, t + 2, S0);
+                        slot(CH1, t, t + 2, S1);
+                    } else {
+                        slot(CH0, t, t + 1, S2);
+                        slot(CH1, t, t + 1, S3);
+                    }
+                }
+                next_drain = T;
+            }
+        }
         TC_PROF_DECL
-        for (int u = g; u < T; u += NWG) {
+        for (int u = sliced ? T : g; u < T; u += NWG) {
             int sv_b = 0;  // DUAL: the V-ring stages of sub-tile u are 2 u (first chunk) and 2 u + 1 (second chunk)
             uint32_t phv_b = 0;
             if constexpr (DUAL) {
@@ -1911,7 +2145,7 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
 }
 
 struct TcPlan {
-    int kb, kp, k_chunks, a_stages, v_stages, nb, la, nwg, wide, splits, tiles_per_split, pair, kv, cg2, dual;
+    int kb, kp, k_chunks, a_stages, v_stages, nb, la, nwg, wide, splits, tiles_per_split, pair, kv, cg2, dual, dual_mode;
     int64_t sub_tiles;
     size_t smem_bytes, vimg_bytes, part_bytes;
 };
@@ -1964,12 +2198,17 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     // Gentries/s -- and loses for d <= 64 (k=1000 133 -> 109, Matern-5/2 d=32 k=200 551 -> 396): the two O buffers are
     // then the two chunks of ONE sub-tile, so a buffer is reused after one sub-tile instead of two and MMA2 waits for a
     // warpgroup that is still in its (long) pointwise stage.  RLAOPT_B200_TC_DUAL: 1 = where it pays (default), 0 = never,
-    // 2 = wherever it is possible.
+    // 2 = wherever it is possible, 3 = as 2, with the SLICED epilogue where three S/P buffers fit (d <= 64): both warpgroups
+    // drain every chunk as it completes and run the pointwise stage of their next sub-tile in quarters between the drains.
+    // That removes the loss for d <= 64 and gains 5-7 % over one chunk per CTA when the chunk count is even (k=1000
+    // 133 -> 143, Matern-5/2 d=32 k=200 545 -> 567 Gentries/s, bit-identical results); it is opt-in because a faster
+    // schedule of the same code (P' announced one slot earlier, 147 Gentries/s) mis-computed about one CTA in 500 for a
+    // reason that is not understood yet (profiles/r02_tc_dual_sliced.md).
     const int dual_env = tc_env_int("RLAOPT_B200_TC_DUAL", 1);
     bool dual = kp == 128 && !wide && k > 128 && kid >= 0 && kid != KID_MATERN12 && (dual_env >= 2 || (dual_env == 1 && kb >= 2)) &&
                 !tc_env_int("RLAOPT_B200_TC_CG2", 0);
     size_t fixed = 8 * TC_BM * sizeof(float) + 64 * sizeof(uint64_t) + 64;
-    if (dual) fixed += 8 * TC_BM * sizeof(float);  // one un-scale factor per row, tile and chunk
+    if (dual) fixed += 8 * TC_BM * sizeof(float) + 2048;  // one un-scale factor per row, tile and chunk; norms of the sliced mode
     // ring depth: 4 stages; deeper rings measured no gain even at one sub-tile per ~600 cycles (RLAOPT_B200_TC_SA)
     int sa = tc_env_int("RLAOPT_B200_TC_SA", 4), sv;
     if (sa < 2) sa = 2;
@@ -1986,7 +2225,7 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
             while (sa > 2 && sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) --sa;
             if (sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) {
                 dual = false;
-                fixed -= 8 * TC_BM * sizeof(float);
+                fixed -= 8 * TC_BM * sizeof(float) + 2048;
                 sv = sa + la;
             }
         }
@@ -2020,6 +2259,9 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     }
     pl->kv = kv;
     pl->dual = dual ? 1 : 0;
+    // sliced mode (the pointwise stage of a sub-tile runs in four slices between the drains of the two sub-tiles before
+    // it): needs three S/P buffers (d <= 64)
+    pl->dual_mode = dual ? ((dual_env >= 3 && nb >= 3) ? 2 : 1) : 0;
     pl->smem_bytes = sa * a_stage + sv * v_stage + fixed;
     const int64_t base = ((n + TC_BM - 1) / TC_BM) * pl->k_chunks;
     const int64_t target = (int64_t)sm_count * 2;
@@ -2224,6 +2466,13 @@ cudaError_t launch_tc(const void* rows_packed, int64_t n, const void* cols_packe
     p.m = m;
     p.k = (int)k;
     p.k_chunks = pl.k_chunks;
+    p.dual_mode = pl.dual_mode;
+    // sliced mode, bits: 1 = quarter loads overlap the drain; 4 = one quarter per slot, P'(u) announced at the end of slot B of
+    // sub-tile u - 1 (the schedule that reproduces the one-chunk kernel bit for bit); 8 = early schedule with the announcement
+    // deferred to the start of that slot; 2 = column norms straight from global memory (diagnostic).  Without bits 4 / 8 the
+    // announcement comes while MMA2 of chunk B of sub-tile u - 1 is still in flight: 10 % faster, and WRONG in about one CTA in
+    // 500 (profiles/r02_tc_dual_sliced.md) -- kept for the investigation only.
+    p.dual_overlap = tc_env_int("RLAOPT_B200_TC_DUAL_OVERLAP", 5);
     p.kb = pl.kb;
     p.nk1 = (int)((d + 15) / 16);
     p.a_stages = pl.a_stages;

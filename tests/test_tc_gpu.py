@@ -337,10 +337,36 @@ def test_two_chunks_per_sub_tile_family(dev, name, n, m, d, k, monkeypatch):
     V = _rand((m, k), 63)
     ref = ko.kernel_matmat_gemm_form(A1, A2, V, name, 1.1, 0.9, dtype=torch.float64)
     outs = []
-    for dual in ("2", "0"):  # 2 = wherever possible (the default uses it for 64 < d <= 128 only), 0 = never
+    # 2 = wherever possible (the default uses it for 64 < d <= 128 only), 3 = sliced schedule where three S/P buffers fit
+    # (d <= 64; elsewhere the same kernels as 2), 0 = never
+    for dual in ("2", "3", "0"):
         monkeypatch.setenv("RLAOPT_B200_TC_DUAL", dual)
         got = kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), name, 1.1, 0.9, layout=LAYOUT_TC)
         assert got.shape == (n, k)
         assert ko.rel_fro_error(got, ref) <= 1e-5, (name, n, m, d, k, dual)
         outs.append(got)
-    assert ko.rel_fro_error(outs[0], outs[1].double().cpu()) <= 2e-6
+    assert ko.rel_fro_error(outs[0], outs[2].double().cpu()) <= 2e-6
+    assert ko.rel_fro_error(outs[1], outs[2].double().cpu()) <= 2e-6
+
+
+@pytest.mark.parametrize("name,n,m,d,k", [("rbf", 20000, 200_000, 64, 512), ("matern52", 9000, 150_000, 32, 256),
+                                          ("rbf", 12000, 100_000, 128, 384)])
+def test_two_chunk_kernels_reproduce_the_one_chunk_kernel_bitwise(dev, name, n, m, d, k, monkeypatch):
+    """The two-chunk kernels do the same arithmetic in the same order as the one-chunk kernel, so the outputs must be
+    IDENTICAL; repeated launches at a size with hundreds of CTAs and column splits.  (An earlier schedule of the sliced
+    mode announced P' while the previous sub-tile's second chunk was still in flight and was wrong in about one CTA in 500
+    -- profiles/r02_tc_dual_sliced.md; this is the test that finds it.)"""
+    from rlaopt_b200._lib import LAYOUT_TC
+    from rlaopt_b200.ops import kernel_matmat
+
+    g = torch.Generator(device=dev).manual_seed(5)
+    A2 = torch.randn(m, d, generator=g, device=dev) / d**0.5
+    V = torch.randn(m, k, generator=g, device=dev)
+    A1 = A2[:n]
+    monkeypatch.setenv("RLAOPT_B200_TC_DUAL", "0")
+    Y0 = kernel_matmat(A1, A2, V, name, 1.0, layout=LAYOUT_TC)
+    for dual in ("1", "2", "3"):
+        monkeypatch.setenv("RLAOPT_B200_TC_DUAL", dual)
+        for _ in range(3):
+            Y = kernel_matmat(A1, A2, V, name, 1.0, layout=LAYOUT_TC)
+            assert torch.equal(Y, Y0), (name, dual, int((Y != Y0).sum()))
