@@ -21,7 +21,8 @@ def run(mode):
     return Y
 Y0 = run("0")
 mode = sys.argv[1] if len(sys.argv) > 1 else "3:0"
-for rep in range(4):
+found = 0
+for rep in range(6):
     Y = run(mode)
     bad = Y != Y0
     if not bool(bad.any()):
@@ -29,25 +30,30 @@ for rep in range(4):
         continue
     rows = torch.unique(bad.nonzero(as_tuple=True)[0])
     blocks = torch.unique(rows // 128)
-    print("rep", rep, "bad row blocks", blocks.numel(), blocks[:12].tolist(), flush=True)
-    for rb in blocks[:4].tolist():
+    print("rep", rep, "bad row blocks", blocks.numel(), blocks[:40].tolist(), flush=True)
+    for rb in blocks[:16].tolist():
         for pair in range(4):
             cs = slice(pair * 256, min((pair + 1) * 256, k))
             sub = bad[rb * 128:(rb + 1) * 128, cs]
             if not bool(sub.any()):
                 continue
-            D = (Y[rb * 128:(rb + 1) * 128, cs] - Y0[rb * 128:(rb + 1) * 128, cs])          # 128 x 256
-            C = (D @ V[:, cs].T) / D.shape[1]                                                # 128 x m: ~ dK[i, m]
-            en = (C * C).view(128, m // 64, 64).sum(dim=(0, 2))                              # energy per sub-tile
-            top = en.topk(6)
+            D = (Y[rb * 128:(rb + 1) * 128, cs] - Y0[rb * 128:(rb + 1) * 128, cs])
+            C = (D @ V[:, cs].T) / D.shape[1]
+            en = (C * C).view(128, m // 64, 64).sum(dim=(0, 2))
+            top = en.topk(3)
             med = float(en.median())
-            print(f"  block {rb} pair {pair}: |D| rms {float(D.pow(2).mean().sqrt()):.3e}; tile energy / median: "
-                  + ", ".join(f"t={int(i)} (u={int(i) % 1024}, split {int(i) // 1024}): {float(v) / med:.1f}" for v, i in zip(top.values, top.indices)), flush=True)
             t0 = int(top.indices[0])
-            x = A1[rb * 128:(rb + 1) * 128].double()
-            Kt = torch.exp(-0.5 * torch.cdist(x, A2[t0 * 64:(t0 + 1) * 64].double()).pow(2))  # 128 x 64
-            rel = (C[:, t0 * 64:(t0 + 1) * 64].double() / Kt)
-            print("    top tile dK/K by column (mean over rows):", [round(float(v), 3) for v in rel.mean(0)], flush=True)
-            print("    top tile dK/K by row (mean over cols, first 16):", [round(float(v), 3) for v in rel.mean(1)[:16]], flush=True)
+            u, sp = t0 % 1024, t0 // 1024
+            T = min(1024, m // 64 - sp * 1024)
+            # which rows / columns of the bad tile carry the error
+            Ct = C[:, t0 * 64:(t0 + 1) * 64]
+            rowe = (Ct * Ct).sum(1); cole = (Ct * Ct).sum(0)
+            print(f"  block {rb} pair {pair}: tile {t0} = split {sp} u {u} of T {T} (u%2 {u % 2} u%3 {u % 3} u%4 {u % 4} u%8 {u % 8}, T-u {T - u}) "
+                  f"energy/median {float(top.values[0]) / med:.1f} next {float(top.values[1]) / med:.1f}; "
+                  f"row quarters {[round(float(rowe[q * 32:(q + 1) * 32].sum() / rowe.sum()), 2) for q in range(4)]} "
+                  f"col quarters {[round(float(cole[q * 16:(q + 1) * 16].sum() / cole.sum()), 2) for q in range(4)]} "
+                  f"|D| chunkA {float(D[:, :128].abs().mean()):.2e} chunkB {float(D[:, 128:].abs().mean()):.2e}", flush=True)
             del C
-    break
+            found += 1
+    if found >= 24:
+        break
