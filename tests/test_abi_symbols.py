@@ -125,6 +125,24 @@ def test_register_contraction_workspace_plan(lib, monkeypatch):
     assert lib.rlaopt_b200_matmat_workspace_bytes(n, m, 500, 1, 4, LAYOUT_TC) >= image  # + split-column partials
 
 
+def test_two_chunk_knob_does_not_change_the_workspace_plan(lib, monkeypatch):
+    """k > 128: whether one CTA contracts one or two 128-column chunks of V per P' (RLAOPT_B200_TC_DUAL) is decided at launch;
+    the V records and the split-column partials are laid out the same way, so a workspace sized under one setting serves
+    every other (the knob is read per launch).  Host-only."""
+    from rlaopt_b200._lib import LAYOUT_TC
+
+    shapes = [(37888, 1_000_000, 128, 256), (94720, 2_000_000, 64, 1000), (1000, 777, 64, 130), (513, 129, 100, 300)]
+    for n, m, d, k in shapes:
+        sizes = set()
+        for dual in (None, "0", "1", "2", "3"):
+            if dual is None:
+                monkeypatch.delenv("RLAOPT_B200_TC_DUAL", raising=False)
+            else:
+                monkeypatch.setenv("RLAOPT_B200_TC_DUAL", dual)
+            sizes.add(lib.rlaopt_b200_matmat_workspace_bytes(n, m, d, k, 4, LAYOUT_TC))
+        assert len(sizes) == 1 and sizes.pop() > 0, (n, m, d, k)
+
+
 def test_torch_library_op_is_registered_from_cpp(lib):
     """``torch.ops.rlaopt.kernel_matmat``: schema defined by TORCH_LIBRARY_FRAGMENT(rlaopt, m) in csrc/torch_op.cpp (the
     reference's registration pattern, rlaopt/csrc/cpp/csc_matmat.cpp:83-87); the CPU key raises -- no CPU fallback."""
