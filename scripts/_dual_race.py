@@ -17,12 +17,16 @@ def run(mode):
     os.environ["RLAOPT_B200_TC_DUAL"] = f[0]
     os.environ["RLAOPT_B200_TC_DUAL_OVERLAP"] = f[1] if len(f) > 1 else "1"
     os.environ["RLAOPT_B200_TC_PAIR"] = f[2] if len(f) > 2 else "-1"
+    if len(f) > 3:
+        os.environ["RLAOPT_B200_TC_SA"] = f[3]  # A-ring depth
+    else:
+        os.environ.pop("RLAOPT_B200_TC_SA", None)
     Y = op @ V
     torch.cuda.synchronize()
     return Y
 Y0 = run("0")
 print("mode 0 repeat identical:", bool((run("0") == Y0).all()), flush=True)
-for mode in sys.argv[1:] or ["3:1", "3:1", "3:17", "3:17", "3:17", "3:17", "3:17", "3:17", "3:16", "3:16", "3:16"]:
+for mode in sys.argv[1:] or ["3:0:-1:2", "3:0:-1:2", "3:0:-1:2", "3:0:-1:2", "3:0", "3:0", "3:0", "3:0", "3:5:-1:2", "3:5:-1:2", "3:5:-1:2"]:
     Y = run(mode)
     bad = (Y != Y0)
     nb = int(bad.sum())
