@@ -1083,9 +1083,16 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             TC_PROF_DECL
             for (int t1 = par; t1 < T; t1 += 2) {
                 TC_PROF(7)
-                // A image landed (CG2: in both CTAs); MMA2 of tile t1 - NB has consumed P[b1]
-                if constexpr (CG2) mbar_wait3(&a_full[sa], pha, &a_peer[sa], pha, &p_free[b1], use1 ^ 1);
-                else mbar_wait2(&a_full[sa], pha, &p_free[b1], use1 ^ 1);
+                // MMA2 of tile t1 - NB has consumed P[b1]; A image landed (CG2: in both CTAs).  p_free FIRST: with an odd ring
+                // depth the two issue warps share the A stages, so the parity wait on a_full is ambiguous while the other
+                // warp's tile t1 - SA is still in flight (it reads "complete"); p_free(t1 - NB) implies that tile has been
+                // consumed.  try_wait suspends the thread up to a system time limit, so a barrier sampled EARLIER in the same
+                // poll can be stale when a later one returns -- the guard has to be sampled first.  (Found with
+                // scripts/tc_protocol_model.py: with the a_full sample first and a suspension of ~6000 cycles MMA1 reads a
+                // stage whose bulk copy has just been issued.  Never observed on the hardware in the shipped kernels; the
+                // race of the experimental early-announce schedule persists with this order, so it has another cause.)
+                if constexpr (CG2) mbar_wait3(&p_free[b1], use1 ^ 1, &a_full[sa], pha, &a_peer[sa], pha);
+                else mbar_wait2(&p_free[b1], use1 ^ 1, &a_full[sa], pha);
                 TC_PROF(0)
                 tc_fence_after();
                 issue_mma1(b1, sa);

@@ -26,7 +26,7 @@ def run(mode):
     return Y
 Y0 = run("0")
 print("mode 0 repeat identical:", bool((run("0") == Y0).all()), flush=True)
-for mode in sys.argv[1:] or ["3:0:-1:2", "3:0:-1:2", "3:0:-1:2", "3:0:-1:2", "3:0", "3:0", "3:0", "3:0", "3:5:-1:2", "3:5:-1:2", "3:5:-1:2"]:
+for mode in sys.argv[1:] or ["3:0", "3:0", "3:0", "3:0", "3:0", "3:0", "3:1", "3:1", "3:1"]:
     Y = run(mode)
     bad = (Y != Y0)
     nb = int(bad.sum())
