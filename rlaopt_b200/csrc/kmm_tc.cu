@@ -1083,16 +1083,25 @@ __global__ void __launch_bounds__(tc_threads(NWG), 1) kmm_tc_kernel(const TcPara
             TC_PROF_DECL
             for (int t1 = par; t1 < T; t1 += 2) {
                 TC_PROF(7)
-                // MMA2 of tile t1 - NB has consumed P[b1]; A image landed (CG2: in both CTAs).  p_free FIRST: with an odd ring
-                // depth the two issue warps share the A stages, so the parity wait on a_full is ambiguous while the other
-                // warp's tile t1 - SA is still in flight (it reads "complete"); p_free(t1 - NB) implies that tile has been
-                // consumed.  try_wait suspends the thread up to a system time limit, so a barrier sampled EARLIER in the same
-                // poll can be stale when a later one returns -- the guard has to be sampled first.  (Found with
-                // scripts/tc_protocol_model.py: with the a_full sample first and a suspension of ~6000 cycles MMA1 reads a
-                // stage whose bulk copy has just been issued.  Never observed on the hardware in the shipped kernels; the
-                // race of the experimental early-announce schedule persists with this order, so it has another cause.)
-                if constexpr (CG2) mbar_wait3(&p_free[b1], use1 ^ 1, &a_full[sa], pha, &a_peer[sa], pha);
-                else mbar_wait2(&p_free[b1], use1 ^ 1, &a_full[sa], pha);
+                // Three conditions, polled in this order:
+                //   a_empty[sa]  MMA1 of the stage's previous tile t1 - SA has completed (the barrier the producer waits on
+                //                before it loads tile t1 into the stage, so it costs nothing);
+                //   p_free[b1]   MMA2 of tile t1 - NB has consumed P[b1];
+                //   a_full[sa]   the image of tile t1 has landed (CG2: in both CTAs).
+                // Why the first: every wait is a PARITY wait, ambiguous by two phases.  With an odd ring depth the two issue
+                // warps share the A stages, so while the OTHER warp's tile t1 - SA is still in flight a_full[sa] reads
+                // "complete" for tile t1.  p_free covers that only when NB <= SA; with NB = 4, SA = 3 (the C2 plan) a bulk copy
+                // that lands ~5000 cycles after its successors would let MMA1 of tile t1 consume the half-landed image of
+                // tile t1 - 3.  a_empty is exact (its previous phase belongs to this warp's own tile t1 - 2 SA, long complete).
+                // Why in this order: try_wait suspends the thread up to a system time limit, so a barrier sampled EARLIER in
+                // the same poll can be stale when a later one returns -- the guards have to be sampled before a_full.
+                // Found with scripts/tc_protocol_model.py (tests/test_tc_protocol_model.py); never observed on the hardware.
+                if constexpr (CG2) {
+                    mbar_wait(&a_empty[sa], pha ^ 1);
+                    mbar_wait3(&p_free[b1], use1 ^ 1, &a_full[sa], pha, &a_peer[sa], pha);
+                } else {
+                    mbar_wait3(&a_empty[sa], pha ^ 1, &p_free[b1], use1 ^ 1, &a_full[sa], pha);
+                }
                 TC_PROF(0)
                 tc_fence_after();
                 issue_mma1(b1, sa);
@@ -2227,6 +2236,12 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     } else {
         while (sa > 2 && sa * a_stage + (sa + la) * v_stage + fixed > (size_t)TC_SMEM_LIMIT) --sa;
         sv = sa + la;
+        // Two epilogue warpgroups own alternate sub-tiles: with an ODD V ring they share its stages, and a warpgroup's
+        // v_full parity wait reads "complete" while the other warpgroup's record of tile u - SV is still in flight.  The
+        // s_full wait of the same poll covers that, but it is sampled after v_full (try_wait may suspend in between).  For
+        // the k > 64 plan {NB 2, SA 2, SV 3} one more stage fits and makes every wait of that kernel unambiguous (the ring
+        // configuration the two-chunk kernels run with); scripts/tc_protocol_model.py, run_single(nb=2, sa=2, sv=3 / 4).
+        if (!dual && nwg == 2 && kp == 128 && (sv & 1) && sa * a_stage + (sv + 1) * v_stage + fixed <= (size_t)TC_SMEM_LIMIT) ++sv;
         if (dual) {  // a sub-tile consumes two V records: at least two sub-tiles in flight
             if (sv < 4) sv = 4;
             while (sa > 2 && sa * a_stage + sv * v_stage + fixed > (size_t)TC_SMEM_LIMIT) --sa;

@@ -54,12 +54,15 @@ class Bar:
 
 
 class Sim:
-    def __init__(self, T, schedule, seed, ooo=False, spike=0.02, try_wait_limit=0, guard_first=True):
+    def __init__(self, T, schedule, seed, ooo=False, spike=0.02, try_wait_limit=0, guard_first=True, nb=NB, sa=SA, sv=SV,
+                 exact_guard=False):
         # try_wait_limit = 0: the barriers of one poll are sampled at the same instant (idealised); > 0: sampled one after
         # the other, each mbarrier.try_wait suspending the thread until its phase completes or the limit (cycles) expires
         # -- a sample taken early in the poll can be stale when the last one returns.  guard_first: order of the two
         # barriers in the MMA1 issue warps' wait (True = p_free then a_full, the kernel since the fix; False = before).
         self.T, self.schedule, self.ooo = T, schedule, ooo
+        self.NB, self.SA, self.SV = nb, sa, sv
+        self.exact_guard = exact_guard
         self.L, self.guard_first = try_wait_limit, guard_first
         self.single = []
         self.rng = random.Random(seed)
@@ -69,20 +72,20 @@ class Sim:
         self.seq = 0
         self.waiters = []  # (agent generator, condition)
         b = lambda c: Bar(c)
-        self.a_full = [b(1) for _ in range(SA)]
-        self.a_empty = [b(1) for _ in range(SA)]
-        self.v_full = [b(1) for _ in range(SV)]
-        self.v_empty = [b(1) for _ in range(SV)]
-        self.s_full = [b(1) for _ in range(NB)]
-        self.p_full = [b(4) for _ in range(NB)]
-        self.p_free = [b(1) for _ in range(NB)]
+        self.a_full = [b(1) for _ in range(self.SA)]
+        self.a_empty = [b(1) for _ in range(self.SA)]
+        self.v_full = [b(1) for _ in range(self.SV)]
+        self.v_empty = [b(1) for _ in range(self.SV)]
+        self.s_full = [b(1) for _ in range(self.NB)]
+        self.p_full = [b(4) for _ in range(self.NB)]
+        self.p_free = [b(1) for _ in range(self.NB)]
         self.o_full = [b(1) for _ in range(2)]
         self.o_free = [b(8) for _ in range(2)]
         # contents
-        self.a_stage = [None] * SA        # tile id, or ("loading", tile)
-        self.v_stage = [None] * SV        # (tile, chunk) or ("loading", ...)
-        self.sp = [None] * NB             # ("S", t, done) / ("P", t, quarters_done_by_warp dict)
-        self.sp_busy = [None] * NB        # tensor op currently writing / reading: (kind, t, end)
+        self.a_stage = [None] * self.SA        # tile id, or ("loading", tile)
+        self.v_stage = [None] * self.SV        # (tile, chunk) or ("loading", ...)
+        self.sp = [None] * self.NB             # ("S", t, done) / ("P", t, quarters_done_by_warp dict)
+        self.sp_busy = [None] * self.NB        # tensor op currently writing / reading: (kind, t, end)
         self.o = [None] * 2               # ("O", t, done)
         self.o_readers = [0, 0]           # drains in progress
         self.pipe_end = 0                 # in-order tensor pipe
@@ -222,26 +225,29 @@ class Sim:
                     self.arrive(self.v_full[s])
                 self.at(self.now + self.load_latency(), vlanded)
                 sv += 1
-                if sv == SV:
+                if sv == self.SV:
                     sv, phv = 0, phv ^ 1
                 yield ("delay", 10)
             sa += 1
-            if sa == SA:
+            if sa == self.SA:
                 sa, pha = 0, pha ^ 1
             yield ("delay", 10)
 
     def mma1(self, par):
-        b1, sa = par % NB, par % SA
-        use1, pha = (par // NB) & 1, (par // SA) & 1
+        b1, sa = par % self.NB, par % self.SA
+        use1, pha = (par // self.NB) & 1, (par // self.SA) & 1
         for t1 in range(par, self.T, 2):
             conds = [(self.p_free[b1], use1 ^ 1), (self.a_full[sa], pha)]
-            yield ("wait", conds if self.guard_first else conds[::-1])
+            conds = conds if self.guard_first else conds[::-1]
+            if self.exact_guard:  # MMA1 of the stage's previous tile has completed (the barrier the producer waits on too)
+                conds.insert(0, (self.a_empty[sa], pha ^ 1))
+            yield ("wait", conds)
 
             def start(s=sa, b=b1, t=t1):
                 if self.a_stage[s] != t:
                     self.fail(f"MMA1({t}) reads A stage {s} holding {self.a_stage[s]}")
                 cur = self.sp[b]
-                if cur is not None and not (cur[0] == "P" and cur[1] == t - NB and cur[2] == "consumed"):
+                if cur is not None and not (cur[0] == "P" and cur[1] == t - self.NB and cur[2] == "consumed"):
                     self.fail(f"MMA1({t}) overwrites S/P buffer {b} holding {cur}")
                 self.sp[b] = ("S", t, False)
 
@@ -252,11 +258,11 @@ class Sim:
             self.issue(("mma1", par), MMA1_CYC, start, end, [self.s_full[b1], self.a_empty[sa]])
             yield ("delay", 60)
             b1 += 2
-            if b1 >= NB:
-                b1, use1 = b1 - NB, use1 ^ 1
+            if b1 >= self.NB:
+                b1, use1 = b1 - self.NB, use1 ^ 1
             sa += 2
-            if sa >= SA:
-                sa, pha = sa - SA, pha ^ 1
+            if sa >= self.SA:
+                sa, pha = sa - self.SA, pha ^ 1
 
     def mma2(self):
         b2 = sv = 0
@@ -289,10 +295,10 @@ class Sim:
                 self.issue("mma2", MMA2_CYC, start, end, commits)
                 yield ("delay", 60)
                 sv += 1
-                if sv == SV:
+                if sv == self.SV:
                     sv, phv = 0, phv ^ 1
             b2 += 1
-            if b2 == NB:
+            if b2 == self.NB:
                 b2, use2 = 0, use2 ^ 1
 
     def epi_warp(self, g, q):
@@ -314,12 +320,12 @@ class Sim:
             self.arrive(self.o_free[ch])
 
         def check_s(u, what):
-            cur = self.sp[u % NB]
+            cur = self.sp[u % self.NB]
             if not cur or cur[1] != u or (cur[0] == "S" and not cur[2]):
-                self.fail(f"warp {g}.{q} {what} of tile {u}: buffer {u % NB} holds {cur}")
+                self.fail(f"warp {g}.{q} {what} of tile {u}: buffer {u % self.NB} holds {cur}")
 
         def slice0(u):
-            yield ("wait", [(self.s_full[u % NB], (u // NB) & 1)])
+            yield ("wait", [(self.s_full[u % self.NB], (u // self.NB) & 1)])
             check_s(u, "reads S")
             yield ("delay", int(650 * speed))
             check_s(u, "writes q0")
@@ -332,7 +338,7 @@ class Sim:
             self.note_quarter(u, g, q, sl)
 
         def announce(u):
-            self.arrive(self.p_full[u % NB])
+            self.arrive(self.p_full[u % self.NB])
 
         def publish(u, defer):
             if defer:
@@ -368,13 +374,134 @@ class Sim:
                             yield from quarter(u, sl)
 
     def note_quarter(self, u, g, q, sl):
-        b = u % NB
+        b = u % self.NB
         cur = self.sp[b]
         if cur[0] == "S":
             cur = ("P", u, {})
         done = cur[2] if isinstance(cur[2], dict) else {}
         done[(q, sl)] = True
         self.sp[b] = ("P", u, "complete" if len(done) == 16 else done)
+
+
+
+class SimSingle(Sim):
+    """The one-chunk kernels (KP <= 64, two epilogue warpgroups that own alternate sub-tiles): per own tile a warpgroup waits
+    for {V record (column norms, V scale), S}, writes P', announces it and drains the O buffer of its previous tile; MMA2
+    contracts one chunk per tile into O[u % 2].  Default rings: the C2 plan (d = 128, k = 64): NB = 4, SA = 3, SV = 5 -- an
+    odd V ring is shared between the two warpgroups, so a warpgroup's v_full parity wait is ambiguous while the OTHER
+    warpgroup's record of tile u - SV is in flight, and the s_full wait of the same poll is its guard.
+    epi_guard_first: s_full polled before v_full (False = the kernel's order, v_full first)."""
+
+    def __init__(self, T, seed, epi_guard_first=False, nb=4, sa=3, sv=5, **kw):
+        super().__init__(T, "single", seed, nb=nb, sa=sa, sv=sv, **kw)
+        self.epi_guard_first = epi_guard_first
+        self.o_free = [Bar(4) for _ in range(2)]
+
+    def producer(self):
+        sa = sv = 0
+        pha = phv = 1
+        for u in range(self.T):
+            yield ("wait", [(self.a_empty[sa], pha)])
+            self.a_stage[sa] = ("loading", u)
+
+            def landed(s=sa, t=u):
+                self.a_stage[s] = t
+                self.arrive(self.a_full[s])
+            self.at(self.now + self.load_latency(), landed)
+            yield ("wait", [(self.v_empty[sv], phv)])
+            self.v_stage[sv] = ("loading", u)
+
+            def vlanded(s=sv, t=u):
+                self.v_stage[s] = (t, 0)
+                self.arrive(self.v_full[s])
+            self.at(self.now + self.load_latency(), vlanded)
+            sa += 1
+            if sa == self.SA:
+                sa, pha = 0, pha ^ 1
+            sv += 1
+            if sv == self.SV:
+                sv, phv = 0, phv ^ 1
+            yield ("delay", 10)
+
+    def mma2(self):
+        b2 = sv = 0
+        use2 = phv = 0
+        for u in range(self.T):
+            ob, opar = u & 1, (u >> 1) & 1
+            yield ("wait", [(self.p_full[b2], use2), (self.v_full[sv], phv), (self.o_free[ob], opar ^ 1)])
+
+            def start(b=b2, s=sv, t=u, o=ob):
+                cur = self.sp[b]
+                if not (cur and cur[0] == "P" and cur[1] == t and cur[2] == "complete"):
+                    self.fail(f"MMA2({t}) reads P' buffer {b} holding {cur}")
+                if self.v_stage[s] != (t, 0):
+                    self.fail(f"MMA2({t}) reads V stage {s} holding {self.v_stage[s]}")
+                if self.o[o] is not None and self.o[o][3] != 4:
+                    self.fail(f"MMA2({t}) overwrites O[{o}] = {self.o[o]} before it was drained")
+                self.o[o] = ("O", t, False, 0)
+
+            def end(b=b2, t=u, o=ob):
+                self.o[o] = ("O", t, True, 0)
+                self.sp[b] = ("P", t, "consumed")
+            self.issue("mma2", MMA1_CYC, start, end, [self.v_empty[sv], self.p_free[b2], self.o_full[ob]])
+            yield ("delay", 60)
+            b2 += 1
+            if b2 == self.NB:
+                b2, use2 = 0, use2 ^ 1
+            sv += 1
+            if sv == self.SV:
+                sv, phv = 0, phv ^ 1
+
+    def epi_warp(self, g, q):
+        speed = 1.0 + 0.05 * q + 0.02 * self.rng.random()
+        for u in range(g, self.T, 2):
+            b, sv = u % self.NB, u % self.SV
+            conds = [(self.v_full[sv], (u // self.SV) & 1), (self.s_full[b], (u // self.NB) & 1)]
+            yield ("wait", conds[::-1] if self.epi_guard_first else conds)
+            if self.v_stage[sv] != (u, 0):
+                self.fail(f"warp {g}.{q} reads the norms of tile {u} from V stage {sv} holding {self.v_stage[sv]}")
+            cur = self.sp[b]
+            if not cur or cur[1] != u or (cur[0] == "S" and not cur[2]):
+                self.fail(f"warp {g}.{q} reads S of tile {u}: buffer {b} holds {cur}")
+            yield ("delay", int(900 * speed))
+            cur = self.sp[b]
+            done = cur[2] if (cur[0] == "P" and isinstance(cur[2], dict)) else {}
+            done[q] = True
+            self.sp[b] = ("P", u, "complete" if len(done) == 4 else done)
+            self.arrive(self.p_full[b])
+            if u >= 2:  # drain the warpgroup's previous tile
+                t = u - 2
+                yield ("wait", [(self.o_full[g], (t >> 1) & 1)])
+                if not (self.o[g] and self.o[g][1] == t and self.o[g][2]):
+                    self.fail(f"warp {g}.{q} drains O[{g}] for tile {t}, holds {self.o[g]}")
+                yield ("delay", int(250 * speed))
+                self.o[g] = self.o[g][:3] + (self.o[g][3] + 1,)
+                self.arrive(self.o_free[g])
+        last = ((self.T - 1 - g) // 2) * 2 + g
+        if self.T > g:
+            yield ("wait", [(self.o_full[g], (last >> 1) & 1)])
+            self.o[g] = self.o[g][:3] + (self.o[g][3] + 1,)
+            self.arrive(self.o_free[g])
+
+
+def run_single(seeds, T, verbose=True, **kw):
+    bad = 0
+    for seed in range(seeds):
+        sim = SimSingle(T, seed, **kw)
+        for agent in (sim.producer(), sim.mma1(0), sim.mma1(1), sim.mma2()):
+            sim.spawn(agent)
+        for g in range(2):
+            for q in range(4):
+                sim.spawn(sim.epi_warp(g, q))
+        try:
+            sim.run()
+        except Violation as e:
+            bad += 1
+            if verbose and bad <= 4:
+                print(f"  seed {seed}: {e}")
+    if verbose:
+        print(f"one-chunk kernel {kw}: {bad} of {seeds} runs violate an invariant (T = {T})")
+    return bad
 
 
 def run(schedule, seeds, T, ooo=False, verbose=True, **kw):
@@ -407,6 +534,11 @@ if __name__ == "__main__":
     seeds = int(args[1]) if len(args) > 1 else 200
     T = int(args[2]) if len(args) > 2 else 40
     limit = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--limit=")), 0)
+    if args and args[0] == "single":
+        for egf in (False, True):
+            for xg in (False, True):
+                run_single(seeds, T, try_wait_limit=limit, epi_guard_first=egf, exact_guard=xg)
+        sys.exit(0)
     for s in scheds:
         if limit:
             for gf in (False, True):

@@ -11,7 +11,7 @@ import tc_protocol_model as M  # noqa: E402
 
 
 def _run(cls, schedule, seed, T=24, ooo=False):
-    sim = cls(T, schedule, seed, ooo=ooo)
+    sim = cls(T, schedule, seed, ooo=ooo, exact_guard=True)
     for agent in (sim.producer(), sim.mma1(0), sim.mma1(1), sim.mma2()):
         sim.spawn(agent)
     for g in range(2):
@@ -61,6 +61,7 @@ def test_model_sees_a_wrong_arrival_count():
 
 
 def _run_kw(schedule, seed, **kw):
+    kw.setdefault("exact_guard", False)  # the two-chunk plan has NB = SA = 3: p_free alone is a sufficient guard there
     sim = M.Sim(24, schedule, seed, **kw)
     for agent in (sim.producer(), sim.mma1(0), sim.mma1(1), sim.mma2()):
         sim.spawn(agent)
@@ -92,3 +93,29 @@ def test_a_full_first_poll_order_is_not():
             assert "MMA1" in str(e) and "A stage" in str(e)
             hits += 1
     assert hits > 0
+
+
+# ---- the one-chunk kernels (two epilogue warpgroups that own alternate sub-tiles), every ring plan tc_plan produces -------
+PLANS_NWG2 = [(2, 2, 4), (3, 3, 4), (4, 3, 5), (4, 4, 6)]  # (NB, SA, SV); {2, 2, 3} is bumped to {2, 2, 4} by the plan
+
+
+@pytest.mark.parametrize("nb,sa,sv", PLANS_NWG2)
+def test_one_chunk_plans_keep_every_data_invariant(nb, sa, sv):
+    assert M.run_single(40, 40, verbose=False, nb=nb, sa=sa, sv=sv, exact_guard=True) == 0
+
+
+def test_c2_plan_needs_the_a_empty_guard():
+    """NB = 4, SA = 3 (d = 128, k = 64): the two MMA1 issue warps share the three A stages, the a_full parity wait is
+    ambiguous while the other warp's tile t - 3 is in flight, and p_free(t - 4) does not cover it.  With the third
+    condition -- a_empty of the stage's previous tile, polled first -- the hole is closed (the kernel's wait)."""
+    assert M.run_single(40, 40, verbose=False, nb=4, sa=3, sv=5, exact_guard=False) > 0
+    assert M.run_single(40, 40, verbose=False, nb=4, sa=3, sv=5, exact_guard=True) == 0
+    assert M.run_single(40, 40, verbose=False, nb=4, sa=3, sv=5, exact_guard=True, try_wait_limit=20000) == 0
+
+
+def test_odd_v_ring_of_the_k128_plan_is_why_it_got_a_fourth_stage():
+    """{NB 2, SA 2, SV 3}: a warpgroup's v_full wait is ambiguous (odd ring shared with the other warpgroup) and sampled
+    before its s_full guard; with suspending try_waits the pointwise stage can read the norms of a record in flight.
+    {2, 2, 4} has no ambiguous wait."""
+    assert M.run_single(60, 40, verbose=False, nb=2, sa=2, sv=3, exact_guard=True, try_wait_limit=20000) > 0
+    assert M.run_single(60, 40, verbose=False, nb=2, sa=2, sv=4, exact_guard=True, try_wait_limit=20000) == 0
