@@ -2194,7 +2194,12 @@ bool tc_plan(int64_t n, int64_t m, int64_t d, int64_t k, int sm_count, TcPlan* p
     // k <= 4 (single right-hand sides: PCG, SAP / ASkotch oracles): the contraction with V runs on the CUDA cores in
     // the epilogue -- one FFMA2 per two entries and column instead of the fp16 split of P, its TMEM store, MMA2 and
     // the accumulator drain.  Three epilogue warpgroups, no CTA pairs.  RLAOPT_B200_TC_KV=0 switches it off.
-    int kv = (!wide && k <= 4 && tc_env_int("RLAOPT_B200_TC_KV", 1)) ? (k == 1 ? 1 : (k == 2 ? 2 : 4)) : 0;
+    // d <= 128 only: with three K-blocks the A ring holds three stages and the plan would be {NB 4, SA 3, SV 5} for three
+    // epilogue warpgroups -- neither ring depth is a multiple of three, so both the s_full and the v_full parity wait of a
+    // warpgroup are ambiguous while another warpgroup's tile is in flight, and nothing in the poll guards them (the V ring
+    // has its own producer in this mode).  scripts/tc_protocol_model.py, run_own(nwg=3, kv=True, nb=4, sa=3, sv=5) finds the
+    // stale reads at once; 128 < d <= 192 takes the MMA2 path with two warpgroups, whose waits are unambiguous.
+    int kv = (!wide && kb <= 2 && k <= 4 && tc_env_int("RLAOPT_B200_TC_KV", 1)) ? (k == 1 ? 1 : (k == 2 ? 2 : 4)) : 0;
     if (kv) nwg = 3;  // a fourth epilogue warpgroup (640 threads, 104 registers) measured 3 % slower at k = 1
     const int x_cols = wide ? 0 : 64 * kb;  // wide d: X streams through smem, only S/P and O live in TMEM
     // TMEM columns: 64 KB (X hi/lo) + 64 NB (S/P) + NWG KP (O) <= 512

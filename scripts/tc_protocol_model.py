@@ -484,6 +484,191 @@ class SimSingle(Sim):
             self.arrive(self.o_free[g])
 
 
+class SimOwn(SimSingle):
+    """Generalisation of SimSingle to NWG epilogue warpgroups owning the sub-tiles u = g (mod NWG) (three for the small-d / k
+    family and the register-contraction mode) and to the register-contraction mode (kv=True: no MMA2 and no O buffers; the
+    epilogue warps release S[b] once it is in registers (p_free, four arrivals) and the V stage once it is read (v_empty,
+    four arrivals); the V ring has its own producer, independent of the A ring)."""
+
+    def __init__(self, T, seed, nwg=3, kv=False, **kw):
+        super().__init__(T, seed, **kw)
+        self.nwg, self.kv = nwg, kv
+        self.o = [None] * nwg
+        self.o_full = [Bar(1) for _ in range(nwg)]
+        self.o_free = [Bar(4) for _ in range(nwg)]
+        if kv:
+            self.p_free = [Bar(4) for _ in range(self.NB)]
+            self.v_empty = [Bar(4) for _ in range(self.SV)]
+
+    def producer(self):
+        if not self.kv:
+            yield from super().producer()
+            return
+        sa, pha = 0, 1
+        for u in range(self.T):
+            yield ("wait", [(self.a_empty[sa], pha)])
+            self.a_stage[sa] = ("loading", u)
+
+            def landed(s=sa, t=u):
+                self.a_stage[s] = t
+                self.arrive(self.a_full[s])
+            self.at(self.now + self.load_latency(), landed)
+            sa += 1
+            if sa == self.SA:
+                sa, pha = 0, pha ^ 1
+            yield ("delay", 10)
+
+    def v_producer(self):
+        sv, phv = 0, 1
+        for u in range(self.T):
+            yield ("wait", [(self.v_empty[sv], phv)])
+            self.v_stage[sv] = ("loading", u)
+
+            def vlanded(s=sv, t=u):
+                self.v_stage[s] = (t, 0)
+                self.arrive(self.v_full[s])
+            self.at(self.now + self.load_latency(), vlanded)
+            sv += 1
+            if sv == self.SV:
+                sv, phv = 0, phv ^ 1
+            yield ("delay", 10)
+
+    def mma1(self, par):
+        if not self.kv:
+            yield from super().mma1(par)
+            return
+        # S[b] is released by the epilogue (p_free) as soon as it is in registers: the buffer's previous content is "read"
+        b1, sa = par % self.NB, par % self.SA
+        use1, pha = (par // self.NB) & 1, (par // self.SA) & 1
+        for t1 in range(par, self.T, 2):
+            conds = [(self.p_free[b1], use1 ^ 1), (self.a_full[sa], pha)]
+            if self.exact_guard:
+                conds.insert(0, (self.a_empty[sa], pha ^ 1))
+            yield ("wait", conds)
+
+            def start(s=sa, b=b1, t=t1):
+                if self.a_stage[s] != t:
+                    self.fail(f"MMA1({t}) reads A stage {s} holding {self.a_stage[s]}")
+                cur = self.sp[b]
+                if cur is not None and not (cur[0] == "R" and cur[1] == t - self.NB and cur[2] == 4):
+                    self.fail(f"MMA1({t}) overwrites S buffer {b} holding {cur}")
+                self.sp[b] = ("S", t, False)
+
+            def end(s=sa, b=b1, t=t1):
+                if self.a_stage[s] != t:
+                    self.fail(f"A stage {s} changed under MMA1({t}): {self.a_stage[s]}")
+                self.sp[b] = ("S", t, True)
+            self.issue(("mma1", par), MMA1_CYC // 2, start, end, [self.s_full[b1], self.a_empty[sa]])
+            yield ("delay", 60)
+            b1 += 2
+            if b1 >= self.NB:
+                b1, use1 = b1 - self.NB, use1 ^ 1
+            sa += 2
+            if sa >= self.SA:
+                sa, pha = sa - self.SA, pha ^ 1
+
+    def mma2(self):
+        if self.kv:
+            return
+            yield
+        b2 = sv = 0
+        use2 = phv = 0
+        for u in range(self.T):
+            ob, opar = u % self.nwg, (u // self.nwg) & 1
+            yield ("wait", [(self.p_full[b2], use2), (self.v_full[sv], phv), (self.o_free[ob], opar ^ 1)])
+
+            def start(b=b2, s=sv, t=u, o=ob):
+                cur = self.sp[b]
+                if not (cur and cur[0] == "P" and cur[1] == t and cur[2] == "complete"):
+                    self.fail(f"MMA2({t}) reads P' buffer {b} holding {cur}")
+                if self.v_stage[s] != (t, 0):
+                    self.fail(f"MMA2({t}) reads V stage {s} holding {self.v_stage[s]}")
+                if self.o[o] is not None and self.o[o][3] != 4:
+                    self.fail(f"MMA2({t}) overwrites O[{o}] = {self.o[o]} before it was drained")
+                self.o[o] = ("O", t, False, 0)
+
+            def end(b=b2, t=u, o=ob):
+                self.o[o] = ("O", t, True, 0)
+                self.sp[b] = ("P", t, "consumed")
+            self.issue("mma2", MMA1_CYC // 2, start, end, [self.v_empty[sv], self.p_free[b2], self.o_full[ob]])
+            yield ("delay", 60)
+            b2 += 1
+            if b2 == self.NB:
+                b2, use2 = 0, use2 ^ 1
+            sv += 1
+            if sv == self.SV:
+                sv, phv = 0, phv ^ 1
+
+    def epi_warp(self, g, q):
+        speed = 1.0 + 0.05 * q + 0.02 * self.rng.random()
+        n = self.nwg
+        for u in range(g, self.T, n):
+            b, sv = u % self.NB, u % self.SV
+            conds = [(self.v_full[sv], (u // self.SV) & 1), (self.s_full[b], (u // self.NB) & 1)]
+            conds = conds[::-1] if self.epi_guard_first else conds
+            if self.epi_exact:  # the buffer's previous tile has been consumed (the barrier MMA1 of this tile waits on)
+                conds.insert(0, (self.p_free[b], ((u // self.NB) & 1) ^ 1))
+            yield ("wait", conds)
+            if self.v_stage[sv] != (u, 0):
+                self.fail(f"warp {g}.{q} reads the norms of tile {u} from V stage {sv} holding {self.v_stage[sv]}")
+            cur = self.sp[b]
+            if not cur or cur[1] != u or (cur[0] == "S" and not cur[2]) or cur[0] == "R" and not self.kv:
+                self.fail(f"warp {g}.{q} reads S of tile {u}: buffer {b} holds {cur}")
+            if self.kv:
+                yield ("delay", int(60 * speed))
+                cur = self.sp[b]
+                cnt = cur[2] + 1 if cur[0] == "R" else 1
+                self.sp[b] = ("R", u, cnt)
+                self.arrive(self.p_free[b])
+                yield ("delay", int(500 * speed))
+                if self.v_stage[sv] != (u, 0):
+                    self.fail(f"V stage {sv} changed under warp {g}.{q} (tile {u}): {self.v_stage[sv]}")
+                self.arrive(self.v_empty[sv])
+                continue
+            yield ("delay", int(600 * speed))
+            cur = self.sp[b]
+            done = cur[2] if (cur[0] == "P" and isinstance(cur[2], dict)) else {}
+            done[q] = True
+            self.sp[b] = ("P", u, "complete" if len(done) == 4 else done)
+            self.arrive(self.p_full[b])
+            if u >= n:
+                t = u - n
+                yield ("wait", [(self.o_full[g], (t // n) & 1)])
+                if not (self.o[g] and self.o[g][1] == t and self.o[g][2]):
+                    self.fail(f"warp {g}.{q} drains O[{g}] for tile {t}, holds {self.o[g]}")
+                yield ("delay", int(150 * speed))
+                self.o[g] = self.o[g][:3] + (self.o[g][3] + 1,)
+                self.arrive(self.o_free[g])
+        if not self.kv and self.T > g:
+            last = ((self.T - 1 - g) // n) * n + g
+            yield ("wait", [(self.o_full[g], (last // n) & 1)])
+            self.o[g] = self.o[g][:3] + (self.o[g][3] + 1,)
+            self.arrive(self.o_free[g])
+
+
+def run_own(seeds, T, verbose=True, epi_exact=False, **kw):
+    bad = 0
+    for seed in range(seeds):
+        sim = SimOwn(T, seed, **kw)
+        sim.epi_exact = epi_exact
+        agents = [sim.producer(), sim.mma1(0), sim.mma1(1)]
+        agents.append(sim.v_producer() if sim.kv else sim.mma2())
+        for a in agents:
+            sim.spawn(a)
+        for g in range(sim.nwg):
+            for q in range(4):
+                sim.spawn(sim.epi_warp(g, q))
+        try:
+            sim.run()
+        except Violation as e:
+            bad += 1
+            if verbose and bad <= 3:
+                print(f"  seed {seed}: {e}")
+    if verbose:
+        print(f"owner-drains kernel {kw} epi_exact={epi_exact}: {bad} of {seeds} runs violate an invariant (T = {T})")
+    return bad
+
+
 def run_single(seeds, T, verbose=True, **kw):
     bad = 0
     for seed in range(seeds):

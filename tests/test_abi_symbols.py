@@ -123,6 +123,9 @@ def test_register_contraction_workspace_plan(lib, monkeypatch):
     # wide d (X streamed through smem) keeps the MMA2 path
     monkeypatch.delenv("RLAOPT_B200_TC_KV", raising=False)
     assert lib.rlaopt_b200_matmat_workspace_bytes(n, m, 500, 1, 4, LAYOUT_TC) >= image  # + split-column partials
+    # 128 < d <= 192: three K-blocks leave ring depths that are ambiguous for three warpgroups -- MMA2 path (tc_plan)
+    assert lib.rlaopt_b200_matmat_workspace_bytes(n, m, 150, 1, 4, LAYOUT_TC) >= image
+    assert lib.rlaopt_b200_matmat_workspace_bytes(n, m, 128, 1, 4, LAYOUT_TC) == sub_tiles * 2 * 256
 
 
 def test_two_chunk_knob_does_not_change_the_workspace_plan(lib, monkeypatch):

@@ -275,9 +275,10 @@ def test_register_contraction_against_fp64_oracle(dev, name, n, m, d, k, monkeyp
         monkeypatch.setenv("RLAOPT_B200_TC_KV", mode)
         got = kernel_matmat(A1.to(dev), A2.to(dev), V.to(dev), name, 1.1, 0.7, layout=LAYOUT_TC)
         assert got.shape == (n, k)
-        assert ko.rel_fro_error(got, ref) <= (2e-6 if mode == "1" else 1e-5), (name, n, m, d, k, mode)
+        tol = 2e-6 if (mode == "1" and d <= 128) else 1e-5  # 128 < d <= 192 takes the MMA2 path in either mode
+        assert ko.rel_fro_error(got, ref) <= tol, (name, n, m, d, k, mode)
         got_t = kernel_matmat(A1.to(dev), A2.to(dev), W.to(dev), name, 1.1, 0.7, transpose=True, layout=LAYOUT_TC)
-        assert ko.rel_fro_error(got_t, ref_t) <= (2e-6 if mode == "1" else 1e-5)
+        assert ko.rel_fro_error(got_t, ref_t) <= tol
 
 
 def test_register_contraction_vector_operand_and_gather(dev, monkeypatch):

@@ -119,3 +119,17 @@ def test_odd_v_ring_of_the_k128_plan_is_why_it_got_a_fourth_stage():
     {2, 2, 4} has no ambiguous wait."""
     assert M.run_single(60, 40, verbose=False, nb=2, sa=2, sv=3, exact_guard=True, try_wait_limit=20000) > 0
     assert M.run_single(60, 40, verbose=False, nb=2, sa=2, sv=4, exact_guard=True, try_wait_limit=20000) == 0
+
+
+# ---- three epilogue warpgroups (small d / k family, register-contraction mode): the plans tc_plan produces --------------
+@pytest.mark.parametrize("kv,nb,sa,sv", [(False, 4, 4, 6), (False, 5, 4, 6), (True, 5, 4, 6)])
+@pytest.mark.parametrize("limit", [0, 20000])
+def test_three_warpgroup_plans_keep_every_data_invariant(kv, nb, sa, sv, limit):
+    assert M.run_own(30, 48, verbose=False, nwg=3, kv=kv, nb=nb, sa=sa, sv=sv, exact_guard=True, try_wait_limit=limit) == 0
+
+
+def test_register_contraction_with_three_k_blocks_is_why_it_stops_at_d_128():
+    """{NB 4, SA 3, SV 5} with three warpgroups (what 128 < d <= 192, k <= 4 would get): both epilogue waits are ambiguous
+    and unguarded -- stale S and stale norms.  tc_plan sends those shapes to the two-warpgroup MMA2 kernels."""
+    assert M.run_own(30, 48, verbose=False, nwg=3, kv=True, nb=4, sa=3, sv=5, exact_guard=True) > 0
+    assert M.run_own(30, 48, verbose=False, nwg=2, kv=False, nb=4, sa=3, sv=5, exact_guard=True) == 0
