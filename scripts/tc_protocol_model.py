@@ -12,6 +12,7 @@ What is modelled (one CTA, no pairs):
       "late"   quarter per slot, P'(u) announced at the end of slot B(u-1)           (shipped, RLAOPT_B200_TC_DUAL_OVERLAP=5)
       "early"  row extreme + q0 | q1 + q2 | q3 + announce | drain only                (the schedule that mis-computes)
       "defer"  as "early", announcement deferred to the start of slot B(u-1)
+      "last"   dual_mode 1 (drains behind the pointwise stage; the default two-chunk kernels, 64 < d <= 128: NB 2, SA 2, SV 4)
   * the contents of every A stage, V stage, S/P buffer and O buffer, checked at every read and write:
       MMA1 reads the image of ITS tile, fully landed;  the pointwise stage reads a complete S of its tile;  MMA2 reads a
       complete P' of its tile and the V record of its chunk;  a drain reads the complete O of its tile and chunk;  nothing
@@ -346,6 +347,28 @@ class Sim:
             else:
                 announce(u)
 
+        if sched == "last":
+            # dual_mode 1 (the default for 64 < d <= 128): a warpgroup runs the whole pointwise stage of its own sub-tile,
+            # announces P', then drains both chunks of every sub-tile up to u - 1 (half of the columns each)
+            nd = 0
+            for u in list(range(g, T, 2)) + [T + g]:
+                if u < T:
+                    sva, svb = (2 * u) % self.SV, (2 * u + 1) % self.SV
+                    yield ("wait", [(self.v_full[sva], ((2 * u) // self.SV) & 1), (self.v_full[svb], ((2 * u + 1) // self.SV) & 1),
+                                    (self.s_full[u % self.NB], (u // self.NB) & 1)])
+                    for ss, cc in ((sva, 0), (svb, 1)):
+                        if self.v_stage[ss] != (u, cc):
+                            self.fail(f"warp {g}.{q} reads the norms / scale of tile {u} from V stage {ss} holding {self.v_stage[ss]}")
+                    check_s(u, "reads S")
+                    yield ("delay", int(1800 * speed))
+                    for sl in range(4):
+                        self.note_quarter(u, g, q, sl)
+                    announce(u)
+                while nd <= min(u - 1, T - 1):
+                    yield from drain(nd, 0)
+                    yield from drain(nd, 1)
+                    nd += 1
+            return
         for t in range(-2, T):
             mine = (t & 1) == g
             if sched == "late":

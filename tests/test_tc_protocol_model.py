@@ -133,3 +133,9 @@ def test_register_contraction_with_three_k_blocks_is_why_it_stops_at_d_128():
     and unguarded -- stale S and stale norms.  tc_plan sends those shapes to the two-warpgroup MMA2 kernels."""
     assert M.run_own(30, 48, verbose=False, nwg=3, kv=True, nb=4, sa=3, sv=5, exact_guard=True) > 0
     assert M.run_own(30, 48, verbose=False, nwg=2, kv=False, nb=4, sa=3, sv=5, exact_guard=True) == 0
+
+
+@pytest.mark.parametrize("nb,sa,sv", [(2, 2, 4), (3, 3, 4)])  # 64 < d <= 128 (default) and d <= 64 (RLAOPT_B200_TC_DUAL=2)
+@pytest.mark.parametrize("limit", [0, 20000])
+def test_drains_last_two_chunk_kernels_keep_every_data_invariant(nb, sa, sv, limit):
+    assert M.run("last", 30, 40, verbose=False, nb=nb, sa=sa, sv=sv, exact_guard=True, try_wait_limit=limit) == 0
